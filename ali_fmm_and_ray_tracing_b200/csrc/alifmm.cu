@@ -1,0 +1,848 @@
+// alifmm.cu -- kernels and C ABI (include/alifmm.h) of the B200 ALI-FMM path.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false
+//             --shared -Xcompiler -fPIC  (see __graft_entry__.build()).
+//
+// Kernels
+//   ali_vmax_kernel      model-wide phase-velocity bound (for the acceptance band delta)
+//   ali_seq_kernel       one warp per source: exact sequential replica of the reference's
+//                        nested near-source grids + main-grid start (ali_seq.cuh)
+//   ali_march_kernel     one CTA per source: band-synchronous narrow-band march
+//                        (ali_band.cuh), lists compacted with warp ballots
+//   ali_finalize_kernel  fine path: T / subgrid (ATR:2832)
+//   ali_rays_kernel      one warp per ray: plane-marching Fermat search (ali_ray.cuh)
+//   ali_curves_kernel / ali_minmax_kernel   material curves and model sanity scan
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <stdlib.h>
+#include <string>
+#include <vector>
+
+#include "../../include/alifmm.h"
+#include "ali_core.cuh"
+#include "ali_seq.cuh"
+#include "ali_band.cuh"
+#include "ali_ray.cuh"
+
+// ---------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static int fail(int code, const std::string &msg)
+{
+    g_last_error = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (expr);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return fail(ALIFMM_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));        \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// device-side per-source records
+// ---------------------------------------------------------------------------
+struct AliSourceRec {
+    int src_iz, src_ix;     // coarse node
+    AliSeqResult seq;       // window + counters of the sequential phase
+    long long rounds, band_evals, band_fallbacks, max_band;
+    int overflow;           // 1: sequential heap/window, 2: band list
+};
+
+struct AliBatch {
+    AliModel m;
+    int sg;
+    int nz, nx;             // extents of the solved grid
+    int margin;
+    double delta;
+    double *T;              // [n_src][nz*nx]
+    uint8_t *st;            // [n_src][nz*nx]
+    // sequential scratch, per source
+    double *seq_t;          // [n_src][2*seq_cap]
+    int32_t *seq_s;         // [n_src][2*seq_cap]
+    int32_t *seq_heap;      // [n_src][2*heap_cap]
+    size_t seq_cap;
+    int heap_cap;
+    // band lists, per source
+    int *lists;             // [n_src][2*band_cap]
+    double *stage;          // [n_src][band_cap]
+    int band_cap;
+    AliSourceRec *rec;      // [n_src]
+};
+
+// ---------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------
+__global__ void ali_vmax_kernel(AliModel m, unsigned long long *out_bits)
+{
+    const size_t n = (size_t)m.nz * m.nx;
+    double best = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        int iz = (int)(i / m.nx), ix = (int)(i % m.nx);
+        double v = ali_node_vmax(m, iz, ix);
+        if (v > best) best = v;
+    }
+    for (int o = 16; o > 0; o >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out_bits, (unsigned long long)__double_as_longlong(best));
+}
+
+__global__ void __launch_bounds__(32) ali_seq_kernel(AliBatch b)
+{
+    const int src = blockIdx.x;
+    const int lane = threadIdx.x;
+    AliSourceRec &rec = b.rec[src];
+    AliSourcePlan p;
+    ali_make_plan(p, b.m, rec.src_iz, rec.src_ix, b.sg, b.margin);
+    AliSeqScratch sc;
+    sc.tA = b.seq_t + (size_t)src * 2 * b.seq_cap;
+    sc.tB = sc.tA + b.seq_cap;
+    sc.sA = b.seq_s + (size_t)src * 2 * b.seq_cap;
+    sc.sB = sc.sA + b.seq_cap;
+    sc.heap = b.seq_heap + (size_t)src * 2 * b.heap_cap;
+    sc.heap_cap = b.heap_cap;
+    sc.status_cap = b.seq_cap;
+    AliSeqResult res;
+    ali_seq_source(b.m, p, sc, b.T + (size_t)src * b.nz * b.nx, res, lane, 32);
+    if (lane == 0) {
+        rec.seq = res;
+        rec.overflow = res.overflow ? 1 : 0;
+    }
+}
+
+// Warp-aggregated append of k (0..4) items per lane to a list with a shared counter.
+__device__ __forceinline__ int ali_warp_reserve(int k, int *counter)
+{
+    const unsigned lane = threadIdx.x & 31;
+    int incl = k;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (unsigned)o) incl += v;
+    }
+    int total = __shfl_sync(0xffffffffu, incl, 31);
+    int base = 0;
+    if (lane == 31 && total > 0) base = atomicAdd(counter, total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    return base + incl - k;
+}
+
+__global__ void __launch_bounds__(1024) ali_march_kernel(AliBatch b)
+{
+    const int src = blockIdx.x;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    AliSourceRec &rec = b.rec[src];
+    __shared__ int s_count[2];
+    __shared__ unsigned long long s_tmin[2];
+    __shared__ int s_overflow;
+    __shared__ unsigned long long s_evals, s_fbs;
+
+    AliBandGrid g;
+    g.nz = b.nz; g.nx = b.nx;
+    g.T = b.T + (size_t)src * b.nz * b.nx;
+    g.st = b.st + (size_t)src * b.nz * b.nx;
+    g.dnx = b.m.dnx;
+    g.mv.scale1 = 1; g.mv.side1 = 0; g.mv.z0 = 0; g.mv.x0 = 0;
+    g.mv.scale0 = b.sg > 1 ? b.sg : 1;
+    g.mv.side0 = b.sg > 1 ? (b.sg - 1) / 2 : 0;
+    g.mv.cast = b.sg > 1 ? 1 : 0;
+    int *list0 = b.lists + (size_t)src * 2 * b.band_cap;
+    int *list1 = list0 + b.band_cap;
+    double *stage = b.stage + (size_t)src * b.band_cap;
+
+    if (tid == 0) {
+        s_count[0] = 0; s_count[1] = 0;
+        s_tmin[0] = ~0ull; s_tmin[1] = ~0ull;
+        s_overflow = rec.overflow;
+        s_evals = 0; s_fbs = 0;
+    }
+    __syncthreads();
+    if (s_overflow) return;
+
+    // hand-over: window statuses of the sequential phase -> byte statuses + first band list
+    {
+        const AliSeqResult w = rec.seq;
+        const int nlev = b.sg > 1 ? 2 : 3;
+        const int32_t *wst = b.seq_s + (size_t)src * 2 * b.seq_cap + ((((nlev - 1) & 1) == 0) ? b.seq_cap : 0);
+        const int wn = w.wnz * w.wnx;
+        for (int base = 0; base < wn; base += nthr) {
+            int i = base + tid;
+            int k = 0, node = 0;
+            if (i < wn) {
+                int z = i / w.wnx, x = i - z * w.wnx;
+                int32_t s = wst[i];
+                node = (w.wz0 + z) * b.nx + (w.wx0 + x);
+                if (s == 0) g.st[node] = ALI_ST_ALIVE;
+                else if (s > 0) { g.st[node] = ALI_ST_BAND; k = 1; }
+            }
+            int pos = ali_warp_reserve(k, &s_count[0]);
+            if (k) {
+                if (pos < b.band_cap) list0[pos] = node;
+                else s_overflow = 2;
+            }
+        }
+    }
+    __syncthreads();
+
+    long long rounds = 0, max_band = 0;
+    unsigned long long my_evals = 0, my_fbs = 0;
+    int cur = 0;
+    while (true) {
+        const int n = s_count[cur];
+        if (n == 0 || s_overflow) break;
+        int *list = cur == 0 ? list0 : list1;
+        int *next = cur == 0 ? list1 : list0;
+        rounds++;
+        if (n > max_band) max_band = n;
+        if (tid == 0) s_tmin[cur ^ 1] = ~0ull;
+        // phase A: evaluate every band node from the round's snapshot
+        for (int i = tid; i < n; i += nthr) {
+            int fb = 0;
+            stage[i] = ali_band_eval(b.m, g, list[i], &fb);
+            my_evals++;
+            my_fbs += fb;
+        }
+        __syncthreads();
+        // phase B: publish + tmin
+        if (tid == 0) s_count[cur] = 0;
+        double lmin = 1e300;
+        for (int i = tid; i < n; i += nthr) {
+            double v = stage[i];
+            ali_band_publish(g, list[i], v);
+            lmin = fmin(lmin, v);
+        }
+        for (int o = 16; o > 0; o >>= 1) lmin = fmin(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+        if ((tid & 31) == 0 && lmin < 1e300)
+            atomicMin(&s_tmin[cur], (unsigned long long)__double_as_longlong(lmin));
+        __syncthreads();
+        // phase C: accept + extend the band, compacting into the other list
+        const double thr = __longlong_as_double((long long)s_tmin[cur]) + b.delta;
+        for (int base = 0; base < n; base += nthr) {
+            int i = base + tid;
+            int k = 0;
+            int out[4];
+            if (i < n) {
+                int node = list[i];
+                if (stage[i] <= thr) {
+                    k = ali_band_accept(g, node, out);
+                } else {
+                    out[0] = node; k = 1;
+                }
+            }
+            int pos = ali_warp_reserve(k, &s_count[cur ^ 1]);
+            if (pos + k <= b.band_cap) {
+                for (int q = 0; q < k; q++) next[pos + q] = out[q];
+            } else if (k) {
+                s_overflow = 2;
+            }
+        }
+        __syncthreads();
+        cur ^= 1;
+    }
+    atomicAdd(&s_evals, my_evals);
+    atomicAdd(&s_fbs, my_fbs);
+    __syncthreads();
+    if (tid == 0) {
+        rec.rounds = rounds;
+        rec.max_band = max_band;
+        rec.band_evals = (long long)s_evals;
+        rec.band_fallbacks = (long long)s_fbs;
+        if (s_overflow) rec.overflow = s_overflow;
+    }
+}
+
+__global__ void ali_finalize_kernel(double *T, size_t n, int sg)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        T[i] = T[i] / sg;
+}
+
+struct AliRayJob {
+    int src_iz, src_ix; // coarse node the ray starts from
+    int rec_slot;       // resident field it is traced through
+};
+
+struct AliRayArgs {
+    AliModel m;
+    int sg, fz, fx;
+    const double *T;            // resident fields
+    const AliSourceRec *rec;    // their sources
+    const AliRayJob *jobs;
+    int n_rays, cap;
+    double *out_x, *out_y, *out_time;
+    int *out_len, *out_flag;
+    int maxc;
+};
+
+#define ALI_RAY_WARPS 4
+__global__ void __launch_bounds__(32 * ALI_RAY_WARPS) ali_rays_kernel(AliRayArgs a)
+{
+    extern __shared__ double s_buf[];
+    __shared__ AliRayState s_state[ALI_RAY_WARPS];
+    __shared__ AliRayPlane s_plane[ALI_RAY_WARPS];
+    __shared__ int s_go[ALI_RAY_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ray = blockIdx.x * ALI_RAY_WARPS + warp;
+    if (ray >= a.n_rays) return;
+    double *TT = s_buf + (size_t)warp * 3 * a.maxc;
+    double *vals = TT + a.maxc;
+    double *poss = vals + a.maxc;
+    AliRayState &s = s_state[warp];
+    AliRayPlane &pl = s_plane[warp];
+    const AliRayJob job = a.jobs[ray];
+    const double *rec = a.T + (size_t)job.rec_slot * a.fz * a.fx;
+    double *ray_x = a.out_x + (size_t)ray * a.cap;
+    double *ray_y = a.out_y + (size_t)ray * a.cap;
+    if (lane == 0) {
+        const AliSourceRec &r = a.rec[job.rec_slot];
+        s.last_x = (double)(a.sg * job.src_ix); s.last_y = (double)(a.sg * job.src_iz);
+        s.rx = (double)(a.sg * r.src_ix); s.ry = (double)(a.sg * r.src_iz);
+        s.lvx = s.rx - s.last_x; s.lvy = s.ry - s.last_y;
+        s.len = 1; s.flag = 0; s.done = 0;
+        ray_x[0] = s.last_x; ray_y[0] = s.last_y;
+    }
+    __syncwarp();
+    while (true) {
+        if (lane == 0) {
+            int go = 0;
+            if (ali_ray_continue(s, a.sg)) {
+                if (s.len >= a.cap - 1) s.flag |= ALI_RAY_CAPACITY;
+                else go = ali_ray_choose_plane(s, a.sg, a.fz, a.fx, pl) ? 1 : 0;
+            }
+            s_go[warp] = go;
+        }
+        __syncwarp();
+        if (!s_go[warp]) break;
+        const double lx = s.last_x, ly = s.last_y;
+        for (int i = lane; i < pl.len; i += 32) TT[i] = ali_ray_candidate_time(a.m, rec, a.fx, pl, i, lx, ly, a.sg);
+        __syncwarp();
+        for (int j = 1 + lane; j < pl.len - 1; j += 32) vals[j] = ali_ray_local_min(TT, j, poss[j]);
+        __syncwarp();
+        if (lane == 0) {
+            double min_i = ali_ray_select(TT, vals, poss, pl.len);
+            s_go[warp] = ali_ray_advance(s, pl, min_i, rec, a.fx, ray_x, ray_y) ? 1 : 0;
+        }
+        __syncwarp();
+        if (!s_go[warp]) break;
+    }
+    if (lane == 0) {
+        ray_x[s.len] = s.rx; ray_y[s.len] = s.ry;
+        s.len += 1;
+    }
+    __syncwarp();
+    // ray_time (ATR:2992-3022): segment times in parallel, summed in path order
+    const int nseg = s.len - 1;
+    double acc = 0.0;
+    for (int base = 0; base < nseg; base += 32) {
+        int i = base + lane;
+        double v = 0.0;
+        if (i < nseg) v = ali_time_between_points(a.m, ray_x[i], ray_x[i + 1], ray_y[i], ray_y[i + 1], a.sg, 1 << 20);
+        TT[lane] = v;
+        __syncwarp();
+        if (lane == 0) {
+            int cnt = nseg - base < 32 ? nseg - base : 32;
+            for (int q = 0; q < cnt; q++) acc += TT[q];
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        a.out_len[ray] = s.len;
+        a.out_time[ray] = acc;
+        a.out_flag[ray] = s.flag;
+    }
+}
+
+// generate_group_vel / generate_phase_vel (ATR:4112-4206): one thread per degree.
+__global__ void ali_curves_kernel(double c22, double c23, double c33, double c44, double rho, double *group,
+                                  double *phase)
+{
+    int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a > 360) return;
+    int angle = a < 180 ? a : a - 180; // 180..360 mirror 0..180 (ATR:4154, 4200); 360 -> 180 -> index 0
+    if (angle >= 180) angle -= 180;
+    double gv, pv;
+    if (angle % 90 == 0) {
+        double lam = (angle % 180 == 90) ? c33 : c22;
+        gv = sqrt(lam / rho);
+        pv = gv;
+    } else {
+        double t = tan(ALI_DEG2RAD * angle);
+        double A = c22 + c33 - 2 * c44;
+        double B = (c23 + c44) * (t - 1 / t);
+        double C = c22 - c33;
+        double disc = sqrt(B * B + A * A - C * C);
+        double ph;
+        if (angle < 90) ph = ali_pymod(atan((-B - disc) / (C - A)), ALI_PI);
+        else ph = ali_pymod(atan((-B + disc) / (C - A)), ALI_PI);
+        double lam = 0.5 * (cos(2 * ph) * (c22 - c44) + sin(2 * ph) * (c23 + c44) * t + c22 + c44);
+        gv = sqrt(lam / rho) / cos(ALI_DEG2RAD * angle - ph);
+        double cs = cos(ALI_DEG2RAD * angle), sn = sin(ALI_DEG2RAD * angle);
+        double A2 = cs * cs * c22 + sn * sn * c44;
+        double B2 = cs * sn * (c23 + c44);
+        double C2 = cs * cs * c44 + sn * sn * c33;
+        pv = sqrt((A2 + C2 + sqrt((A2 - C2) * (A2 - C2) + 4 * (B2 * B2))) / (2 * rho));
+    }
+    group[a] = gv;
+    phase[a] = pv;
+}
+
+// min_max_vel (ATR:3736-3787): group velocity at 0/45/90/135 degrees per node (Christoffel
+// models, decided by velpn[0,0] as in the reference) or table column extrema.
+__global__ void ali_minmax_kernel(AliModel m, int first_velpn, const double *col_min, const double *col_max,
+                                  unsigned long long *min_bits, unsigned long long *max_bits)
+{
+    const size_t n = (size_t)m.nz * m.nx;
+    double lo = 1e300, hi = 0.0;
+    const AliMatView idv = ali_view_identity();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        int iz = (int)(i / m.nx), ix = (int)(i % m.nx);
+        AliMat mat;
+        ali_fetch_mat(m, idv, iz, ix, mat, true);
+        if (first_velpn == 0) {
+            for (int q = 0; q < 4; q++) {
+                double v = ali_christoffel_group(45.0 * q, mat.s, mat.vel_map);
+                lo = fmin(lo, v); hi = fmax(hi, v);
+            }
+        } else {
+            lo = fmin(lo, mat.vel_map * col_min[mat.velpn]);
+            hi = fmax(hi, mat.vel_map * col_max[mat.velpn]);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(min_bits, (unsigned long long)__double_as_longlong(lo));
+        atomicMax(max_bits, (unsigned long long)__double_as_longlong(hi));
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host side: context
+// ---------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+};
+
+struct alifmm_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    AliModel m{};           // device pointers
+    int nz = 0, nx = 0;
+    std::vector<void *> model_allocs;
+    double vmax = 0.0;
+    // options
+    double delta_frac = 0.25;
+    int margin = 27;
+    double band_cap_factor = 6.0;
+    int threads_per_source = 1024;
+    // resident batch
+    int n_slots = 0, sg = 0, fz = 0, fx = 0;
+    DevBuf T, st, seq_t, seq_s, seq_heap, lists, stage, rec, jobs, ray_x, ray_y, ray_time, ray_len, ray_flag, misc;
+    alifmm_counters_t cnt{};
+};
+
+static int dev_reserve(DevBuf &b, size_t bytes)
+{
+    if (b.bytes >= bytes && b.p) return ALIFMM_OK;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr; b.bytes = 0;
+    cudaError_t e = cudaMalloc(&b.p, bytes);
+    if (e != cudaSuccess) return fail(ALIFMM_E_CUDA, std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
+    b.bytes = bytes;
+    return ALIFMM_OK;
+}
+
+static void dev_release(DevBuf &b)
+{
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr; b.bytes = 0;
+}
+
+template <class Tp>
+static int upload(alifmm_ctx *c, const Tp *host, size_t n, const Tp **dev_out)
+{
+    void *d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, n * sizeof(Tp)));
+    c->model_allocs.push_back(d);
+    CUDA_TRY(cudaMemcpyAsync(d, host, n * sizeof(Tp), cudaMemcpyHostToDevice, c->stream));
+    *dev_out = (const Tp *)d;
+    return ALIFMM_OK;
+}
+
+extern "C" const char *alifmm_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int alifmm_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" void alifmm_destroy(alifmm_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (void *p : c->model_allocs) cudaFree(p);
+    DevBuf *bufs[] = {&c->T, &c->st, &c->seq_t, &c->seq_s, &c->seq_heap, &c->lists, &c->stage, &c->rec, &c->jobs,
+                      &c->ray_x, &c->ray_y, &c->ray_time, &c->ray_len, &c->ray_flag, &c->misc};
+    for (DevBuf *b : bufs) dev_release(*b);
+    for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+extern "C" int alifmm_create(const alifmm_model_desc *d, int device, alifmm_ctx **out)
+{
+    if (!d || !out) return fail(ALIFMM_E_INVALID, "alifmm_create: null argument");
+    if (d->nz < 1 || d->nx < 1 || !(d->dnx > 0) || !d->veln || !d->velpn || !d->vel_map || !d->group_vel ||
+        !d->phase_vel || d->n_cols < 1)
+        return fail(ALIFMM_E_INVALID, "alifmm_create: bad model descriptor");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(ALIFMM_E_CUDA, "alifmm_create: no CUDA device available (this library has no CPU path)");
+    }
+    if (device < 0 || device >= ndev) return fail(ALIFMM_E_INVALID, "alifmm_create: device index out of range");
+    CUDA_TRY(cudaSetDevice(device));
+    alifmm_ctx *c = new alifmm_ctx();
+    c->device = device;
+    int rc = ALIFMM_OK;
+    auto bail = [&](int code) { alifmm_destroy(c); return code; };
+    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess)
+        return bail(fail(ALIFMM_E_CUDA, "cudaStreamCreate failed"));
+    c->stream = c->own_stream;
+    for (auto &ev : c->ev)
+        if (cudaEventCreate(&ev) != cudaSuccess) return bail(fail(ALIFMM_E_CUDA, "cudaEventCreate failed"));
+    const size_t n = (size_t)d->nz * d->nx;
+    c->nz = d->nz; c->nx = d->nx;
+    c->m.nz = d->nz; c->m.nx = d->nx; c->m.dnx = d->dnx; c->m.ncol = d->n_cols;
+    c->m.has_stif = d->has_stif ? 1 : 0;
+    if ((rc = upload(c, d->veln, n, &c->m.veln)) != 0) return bail(rc);
+    if ((rc = upload(c, d->velpn, n, &c->m.velpn)) != 0) return bail(rc);
+    if ((rc = upload(c, d->vel_map, n, &c->m.vel_map)) != 0) return bail(rc);
+    c->m.stif = nullptr;
+    if (d->stif_den) {
+        const long long *dp = nullptr;
+        if ((rc = upload(c, (const long long *)d->stif_den, n * 5, &dp)) != 0) return bail(rc);
+        c->m.stif = dp;
+    }
+    if ((rc = upload(c, d->group_vel, (size_t)361 * d->n_cols, &c->m.group_tab)) != 0) return bail(rc);
+    if ((rc = upload(c, d->phase_vel, (size_t)361 * d->n_cols, &c->m.phase_tab)) != 0) return bail(rc);
+    // material ids must index the tables
+    // (validated on the host: an out-of-range id would read outside the table on the device)
+    for (size_t i = 0; i < n; i++)
+        if (d->velpn[i] < 0 || d->velpn[i] >= d->n_cols)
+            return bail(fail(ALIFMM_E_INVALID, "alifmm_create: velpn holds a material id outside the velocity tables"));
+    // model-wide phase-velocity bound
+    if ((rc = dev_reserve(c->misc, 64)) != 0) return bail(rc);
+    if (cudaMemsetAsync(c->misc.p, 0, 64, c->stream) != cudaSuccess) return bail(fail(ALIFMM_E_CUDA, "memset failed"));
+    {
+        int blocks = (int)((n + 255) / 256);
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        ali_vmax_kernel<<<blocks, 256, 0, c->stream>>>(c->m, (unsigned long long *)c->misc.p);
+    }
+    unsigned long long bits = 0;
+    if (cudaMemcpyAsync(&bits, c->misc.p, 8, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+        cudaStreamSynchronize(c->stream) != cudaSuccess) {
+        cudaError_t le = cudaGetLastError();
+        return bail(fail(ALIFMM_E_CUDA, std::string("alifmm_create: vmax kernel failed: ") + cudaGetErrorString(le)));
+    }
+    memcpy(&c->vmax, &bits, 8);
+    if (!(c->vmax > 0) || !isfinite(c->vmax))
+        return bail(fail(ALIFMM_E_INVALID, "alifmm_create: model has no positive finite phase velocity"));
+    c->cnt.vmax = c->vmax;
+    *out = c;
+    return ALIFMM_OK;
+}
+
+extern "C" int alifmm_set_option(alifmm_ctx *c, const char *name, double value)
+{
+    if (!c || !name) return fail(ALIFMM_E_INVALID, "alifmm_set_option: null argument");
+    if (!strcmp(name, "delta_frac")) {
+        if (!(value > 0 && value <= 0.4)) return fail(ALIFMM_E_INVALID, "delta_frac must be in (0, 0.4]");
+        c->delta_frac = value;
+    } else if (!strcmp(name, "handover_margin")) {
+        if (value < 4 || value > 100000) return fail(ALIFMM_E_INVALID, "handover_margin must be >= 4");
+        c->margin = (int)value;
+    } else if (!strcmp(name, "band_capacity_factor")) {
+        if (!(value >= 1 && value <= 1024)) return fail(ALIFMM_E_INVALID, "band_capacity_factor must be in [1, 1024]");
+        c->band_cap_factor = value;
+    } else if (!strcmp(name, "threads_per_source")) {
+        int t = (int)value;
+        if (t < 32 || t > 1024 || (t & 31)) return fail(ALIFMM_E_INVALID, "threads_per_source must be a multiple of 32 in [32, 1024]");
+        c->threads_per_source = t;
+    } else {
+        return fail(ALIFMM_E_INVALID, std::string("unknown option ") + name);
+    }
+    return ALIFMM_OK;
+}
+
+extern "C" int alifmm_set_stream(alifmm_ctx *c, void *s)
+{
+    if (!c) return fail(ALIFMM_E_INVALID, "alifmm_set_stream: null context");
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return ALIFMM_OK;
+}
+
+extern "C" int alifmm_ttf(alifmm_ctx *c, int32_t n_src, const int32_t *src_iz, const int32_t *src_ix, int32_t sg,
+                          double *out_host)
+{
+    if (!c || !src_iz || !src_ix) return fail(ALIFMM_E_INVALID, "alifmm_ttf: null argument");
+    if (n_src < 1) return fail(ALIFMM_E_INVALID, "alifmm_ttf: n_src must be >= 1");
+    if (sg < 1 || (sg & 1) == 0) return fail(ALIFMM_E_INVALID, "alifmm_ttf: subgrid must be odd and >= 1");
+    for (int k = 0; k < n_src; k++)
+        if (src_iz[k] < 0 || src_iz[k] >= c->nz || src_ix[k] < 0 || src_ix[k] >= c->nx)
+            return fail(ALIFMM_E_INVALID, "alifmm_ttf: source node outside the grid");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const int fz = sg > 1 ? sg * (c->nz - 1) + 1 : c->nz;
+    const int fx = sg > 1 ? sg * (c->nx - 1) + 1 : c->nx;
+    if ((long long)fz * fx > 2147483000LL) return fail(ALIFMM_E_INVALID, "alifmm_ttf: grid has more than 2^31 nodes");
+    const size_t N = (size_t)fz * fx;
+
+    AliBatch b;
+    b.m = c->m; b.sg = sg; b.nz = fz; b.nx = fx; b.margin = c->margin;
+    b.delta = c->delta_frac * c->m.dnx / c->vmax;
+    {   // scratch sizes from the plan (same for every source)
+        AliSourcePlan p;
+        ali_make_plan(p, c->m, 0, 0, sg, c->margin);
+        size_t lvl = ali_plan_max_level_nodes(p);
+        size_t w = (size_t)(2 * (p.stop_r + 4) + 1);
+        size_t cap = lvl > w * w ? lvl : w * w;
+        b.seq_cap = cap;
+        b.heap_cap = (int)(cap / 2 + 64);
+    }
+    b.band_cap = (int)(c->band_cap_factor * (double)(fz + fx)) + 1024;
+    int rc;
+    if ((rc = dev_reserve(c->T, (size_t)n_src * N * sizeof(double))) != 0) return rc;
+    if ((rc = dev_reserve(c->st, (size_t)n_src * N + 16)) != 0) return rc;
+    if ((rc = dev_reserve(c->seq_t, (size_t)n_src * 2 * b.seq_cap * sizeof(double))) != 0) return rc;
+    if ((rc = dev_reserve(c->seq_s, (size_t)n_src * 2 * b.seq_cap * sizeof(int32_t))) != 0) return rc;
+    if ((rc = dev_reserve(c->seq_heap, (size_t)n_src * 2 * b.heap_cap * sizeof(int32_t))) != 0) return rc;
+    if ((rc = dev_reserve(c->lists, (size_t)n_src * 2 * b.band_cap * sizeof(int))) != 0) return rc;
+    if ((rc = dev_reserve(c->stage, (size_t)n_src * b.band_cap * sizeof(double))) != 0) return rc;
+    if ((rc = dev_reserve(c->rec, (size_t)n_src * sizeof(AliSourceRec))) != 0) return rc;
+    b.T = (double *)c->T.p; b.st = (uint8_t *)c->st.p;
+    b.seq_t = (double *)c->seq_t.p; b.seq_s = (int32_t *)c->seq_s.p; b.seq_heap = (int32_t *)c->seq_heap.p;
+    b.lists = (int *)c->lists.p; b.stage = (double *)c->stage.p; b.rec = (AliSourceRec *)c->rec.p;
+
+    std::vector<AliSourceRec> recs(n_src);
+    memset(recs.data(), 0, recs.size() * sizeof(AliSourceRec));
+    for (int k = 0; k < n_src; k++) { recs[k].src_iz = src_iz[k]; recs[k].src_ix = src_ix[k]; }
+    c->n_slots = 0;
+    cudaStream_t s = c->stream;
+    CUDA_TRY(cudaMemcpyAsync(b.rec, recs.data(), recs.size() * sizeof(AliSourceRec), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaEventRecord(c->ev[0], s));
+    CUDA_TRY(cudaMemsetAsync(b.T, 0, (size_t)n_src * N * sizeof(double), s));
+    CUDA_TRY(cudaMemsetAsync(b.st, 0, (size_t)n_src * N, s));
+    ali_seq_kernel<<<n_src, 32, 0, s>>>(b);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(c->ev[1], s));
+    ali_march_kernel<<<n_src, c->threads_per_source, 0, s>>>(b);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(c->ev[2], s));
+    int launches = 2;
+    if (sg > 1) {
+        size_t total = (size_t)n_src * N;
+        int blocks = (int)((total + 255) / 256);
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        ali_finalize_kernel<<<blocks, 256, 0, s>>>(b.T, total, sg);
+        CUDA_TRY(cudaGetLastError());
+        launches++;
+    }
+    CUDA_TRY(cudaEventRecord(c->ev[3], s));
+    CUDA_TRY(cudaMemcpyAsync(recs.data(), b.rec, recs.size() * sizeof(AliSourceRec), cudaMemcpyDeviceToHost, s));
+    if (out_host)
+        CUDA_TRY(cudaMemcpyAsync(out_host, b.T, (size_t)n_src * N * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+
+    alifmm_counters_t &cn = c->cnt;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); cn.ms_seq = ms;
+    cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); cn.ms_march = ms;
+    cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); cn.ms_finalize = ms;
+    cn.node_solves = (int64_t)n_src * (int64_t)N;
+    cn.seq_pops = cn.seq_evals = cn.band_rounds = cn.band_rounds_max = cn.band_evals = cn.fallback_evals = cn.max_band = 0;
+    cn.kernel_launches = launches;
+    cn.delta = b.delta;
+    int overflow = 0;
+    for (const AliSourceRec &r : recs) {
+        cn.seq_pops += r.seq.cnt.pops;
+        cn.seq_evals += r.seq.cnt.evals;
+        cn.fallback_evals += r.seq.cnt.fallbacks + r.band_fallbacks;
+        cn.band_rounds += r.rounds;
+        if (r.rounds > cn.band_rounds_max) cn.band_rounds_max = r.rounds;
+        cn.band_evals += r.band_evals;
+        if (r.max_band > cn.max_band) cn.max_band = r.max_band;
+        overflow |= r.overflow;
+    }
+    if (overflow & 2)
+        return fail(ALIFMM_E_CAPACITY, "alifmm_ttf: narrow-band list overflowed; raise option band_capacity_factor");
+    if (overflow & 1)
+        return fail(ALIFMM_E_CAPACITY, "alifmm_ttf: sequential near-source scratch overflowed");
+    c->n_slots = n_src; c->sg = sg; c->fz = fz; c->fx = fx;
+    return ALIFMM_OK;
+}
+
+extern "C" int alifmm_ttf_shape(alifmm_ctx *c, int32_t *n_slots, int32_t *fz, int32_t *fx, int32_t *sg)
+{
+    if (!c) return fail(ALIFMM_E_INVALID, "alifmm_ttf_shape: null context");
+    if (n_slots) *n_slots = c->n_slots;
+    if (fz) *fz = c->fz;
+    if (fx) *fx = c->fx;
+    if (sg) *sg = c->sg;
+    return ALIFMM_OK;
+}
+
+extern "C" int alifmm_ttf_fetch(alifmm_ctx *c, int32_t slot, double *out_host)
+{
+    if (!c || !out_host) return fail(ALIFMM_E_INVALID, "alifmm_ttf_fetch: null argument");
+    if (slot < 0 || slot >= c->n_slots) return fail(ALIFMM_E_STATE, "alifmm_ttf_fetch: no such resident field");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const size_t N = (size_t)c->fz * c->fx;
+    CUDA_TRY(cudaMemcpyAsync(out_host, (double *)c->T.p + (size_t)slot * N, N * sizeof(double),
+                             cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ALIFMM_OK;
+}
+
+extern "C" int alifmm_rays(alifmm_ctx *c, int32_t n_rays, const int32_t *src_iz, const int32_t *src_ix,
+                           const int32_t *rec_slot, int32_t cap, double *out_x, double *out_y, int32_t *out_len,
+                           double *out_time, int32_t *out_flag)
+{
+    if (!c || !src_iz || !src_ix || !rec_slot || !out_len || !out_time)
+        return fail(ALIFMM_E_INVALID, "alifmm_rays: null argument");
+    if (c->n_slots < 1) return fail(ALIFMM_E_STATE, "alifmm_rays: no resident travel-time fields (call alifmm_ttf first)");
+    if (n_rays < 1) return fail(ALIFMM_E_INVALID, "alifmm_rays: n_rays must be >= 1");
+    if (cap < 4) return fail(ALIFMM_E_INVALID, "alifmm_rays: capacity too small");
+    std::vector<AliRayJob> jobs(n_rays);
+    for (int r = 0; r < n_rays; r++) {
+        if (rec_slot[r] < 0 || rec_slot[r] >= c->n_slots) return fail(ALIFMM_E_INVALID, "alifmm_rays: rec_slot out of range");
+        if (src_iz[r] < 0 || src_iz[r] >= c->nz || src_ix[r] < 0 || src_ix[r] >= c->nx)
+            return fail(ALIFMM_E_INVALID, "alifmm_rays: source node outside the grid");
+        jobs[r].src_iz = src_iz[r]; jobs[r].src_ix = src_ix[r]; jobs[r].rec_slot = rec_slot[r];
+    }
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = dev_reserve(c->jobs, (size_t)n_rays * sizeof(AliRayJob))) != 0) return rc;
+    if ((rc = dev_reserve(c->ray_x, (size_t)n_rays * cap * sizeof(double))) != 0) return rc;
+    if ((rc = dev_reserve(c->ray_y, (size_t)n_rays * cap * sizeof(double))) != 0) return rc;
+    if ((rc = dev_reserve(c->ray_time, (size_t)n_rays * sizeof(double))) != 0) return rc;
+    if ((rc = dev_reserve(c->ray_len, (size_t)n_rays * sizeof(int))) != 0) return rc;
+    if ((rc = dev_reserve(c->ray_flag, (size_t)n_rays * sizeof(int))) != 0) return rc;
+    AliRayArgs a;
+    a.m = c->m; a.sg = c->sg; a.fz = c->fz; a.fx = c->fx;
+    a.T = (const double *)c->T.p; a.rec = (const AliSourceRec *)c->rec.p; a.jobs = (const AliRayJob *)c->jobs.p;
+    a.n_rays = n_rays; a.cap = cap;
+    a.out_x = (double *)c->ray_x.p; a.out_y = (double *)c->ray_y.p; a.out_time = (double *)c->ray_time.p;
+    a.out_len = (int *)c->ray_len.p; a.out_flag = (int *)c->ray_flag.p;
+    a.maxc = ali_ray_max_candidates(c->sg);
+    if (a.maxc < 32) a.maxc = 32;
+    cudaStream_t s = c->stream;
+    CUDA_TRY(cudaMemcpyAsync(c->jobs.p, jobs.data(), jobs.size() * sizeof(AliRayJob), cudaMemcpyHostToDevice, s));
+    const size_t smem = (size_t)ALI_RAY_WARPS * 3 * a.maxc * sizeof(double);
+    if (smem > 48 * 1024) {
+        if (smem > 200 * 1024) return fail(ALIFMM_E_INVALID, "alifmm_rays: subgrid too large for the ray kernel's shared memory");
+        CUDA_TRY(cudaFuncSetAttribute(ali_rays_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    CUDA_TRY(cudaEventRecord(c->ev[3], s));
+    ali_rays_kernel<<<(n_rays + ALI_RAY_WARPS - 1) / ALI_RAY_WARPS, 32 * ALI_RAY_WARPS, smem, s>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(c->ev[4], s));
+    CUDA_TRY(cudaMemcpyAsync(out_len, a.out_len, (size_t)n_rays * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(out_time, a.out_time, (size_t)n_rays * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (out_flag) CUDA_TRY(cudaMemcpyAsync(out_flag, a.out_flag, (size_t)n_rays * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (out_x) CUDA_TRY(cudaMemcpyAsync(out_x, a.out_x, (size_t)n_rays * cap * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (out_y) CUDA_TRY(cudaMemcpyAsync(out_y, a.out_y, (size_t)n_rays * cap * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]);
+    c->cnt.ms_rays = ms;
+    c->cnt.rays = n_rays;
+    c->cnt.ray_points = 0;
+    for (int r = 0; r < n_rays; r++) c->cnt.ray_points += out_len[r];
+    c->cnt.kernel_launches = 1;
+    return ALIFMM_OK;
+}
+
+extern "C" int alifmm_mem_info(alifmm_ctx *c, int64_t *free_bytes, int64_t *total_bytes)
+{
+    if (!c) return fail(ALIFMM_E_INVALID, "alifmm_mem_info: null context");
+    CUDA_TRY(cudaSetDevice(c->device));
+    size_t f = 0, t = 0;
+    CUDA_TRY(cudaMemGetInfo(&f, &t));
+    if (free_bytes) *free_bytes = (int64_t)f;
+    if (total_bytes) *total_bytes = (int64_t)t;
+    return ALIFMM_OK;
+}
+
+extern "C" int alifmm_counters(alifmm_ctx *c, alifmm_counters_t *out)
+{
+    if (!c || !out) return fail(ALIFMM_E_INVALID, "alifmm_counters: null argument");
+    *out = c->cnt;
+    return ALIFMM_OK;
+}
+
+extern "C" int alifmm_velocity_curves(alifmm_ctx *c, double c22, double c23, double c33, double c44, double density,
+                                      double *group_out, double *phase_out)
+{
+    if (!c || !group_out || !phase_out) return fail(ALIFMM_E_INVALID, "alifmm_velocity_curves: null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = dev_reserve(c->misc, 2 * 361 * sizeof(double) + 64)) != 0) return rc;
+    double *g = (double *)((char *)c->misc.p + 64), *p = g + 361;
+    ali_curves_kernel<<<3, 128, 0, c->stream>>>(c22, c23, c33, c44, density, g, p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(group_out, g, 361 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(phase_out, p, 361 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ALIFMM_OK;
+}
+
+extern "C" int alifmm_min_max_vel(alifmm_ctx *c, double *min_vel, double *max_vel)
+{
+    if (!c || !min_vel || !max_vel) return fail(ALIFMM_E_INVALID, "alifmm_min_max_vel: null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    // column extrema of the group table over all 361 rows (ATR:3755-3759) on the host: tiny
+    std::vector<double> tab((size_t)361 * c->m.ncol), cmin(c->m.ncol), cmax(c->m.ncol);
+    CUDA_TRY(cudaMemcpy(tab.data(), c->m.group_tab, tab.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < c->m.ncol; k++) {
+        double lo = tab[k], hi = tab[k];
+        for (int a = 1; a < 361; a++) {
+            double v = tab[(size_t)a * c->m.ncol + k];
+            if (v < lo) lo = v;
+            if (v > hi) hi = v;
+        }
+        cmin[k] = lo; cmax[k] = hi;
+    }
+    int first = 0;
+    CUDA_TRY(cudaMemcpy(&first, c->m.velpn, sizeof(int), cudaMemcpyDeviceToHost));
+    int rc;
+    const size_t need = 64 + 2 * (size_t)c->m.ncol * sizeof(double);
+    if ((rc = dev_reserve(c->misc, need > 2 * 361 * sizeof(double) + 64 ? need : 2 * 361 * sizeof(double) + 64)) != 0) return rc;
+    unsigned long long init[2] = {~0ull, 0ull};
+    double *dmin = (double *)((char *)c->misc.p + 64), *dmax = dmin + c->m.ncol;
+    CUDA_TRY(cudaMemcpyAsync(c->misc.p, init, 16, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(dmin, cmin.data(), cmin.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(dmax, cmax.data(), cmax.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    const size_t n = (size_t)c->nz * c->nx;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    ali_minmax_kernel<<<blocks, 256, 0, c->stream>>>(c->m, first, dmin, dmax, (unsigned long long *)c->misc.p,
+                                                     (unsigned long long *)c->misc.p + 1);
+    CUDA_TRY(cudaGetLastError());
+    unsigned long long res[2];
+    CUDA_TRY(cudaMemcpyAsync(res, c->misc.p, 16, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    memcpy(min_vel, &res[0], 8);
+    memcpy(max_vel, &res[1], 8);
+    return ALIFMM_OK;
+}

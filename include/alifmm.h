@@ -1,0 +1,139 @@
+/*
+ * alifmm.h -- C ABI of the B200 ALI-FMM travel-time-field + ray-tracing path.
+ *
+ * The reference (WiPi-UoS/ALI-FMM-and-ray-tracing, Anis_TTF_rays.py = "ATR") has no FFI
+ * layer: its hot path is numba-jitted Python called from class ALI_FMM (ATR:3789-4705).
+ * This header is the boundary a maintainer binds instead (ctypes stub in
+ * INTEGRATION.md).  Every entry point names the reference interface it replaces.
+ *
+ * Conventions: all pointers are caller-owned HOST memory, C-contiguous, row-major
+ * [z][x]; sizes are element counts; functions return 0 on success and a negative
+ * ALIFMM_E_* code on failure, with a message available from alifmm_last_error()
+ * (thread-local).  A context is bound to one CUDA device and must be used by one
+ * thread at a time.  There is no CPU fallback: without a usable device
+ * alifmm_create() fails.
+ */
+#ifndef ALIFMM_H
+#define ALIFMM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ALIFMM_OK 0
+#define ALIFMM_E_INVALID (-1)   /* bad argument */
+#define ALIFMM_E_CUDA (-2)      /* CUDA runtime error (no device, out of memory, launch failure) */
+#define ALIFMM_E_CAPACITY (-3)  /* an internal work list overflowed (see alifmm_set_option) */
+#define ALIFMM_E_STATE (-4)     /* call order (e.g. rays before any field was computed) */
+
+typedef struct alifmm_ctx alifmm_ctx;
+
+/* The model arrays ALI_FMM.__init__ / update take (ATR:3793, 3870):
+ *   veln     orientation in degrees              float64 [nz*nx]
+ *   velpn    material id, 0 = stiffness tensors  int32   [nz*nx]
+ *   vel_map  velocity scale                      float64 [nz*nx]
+ *   stif_den (c22,c23,c33,c44 [MPa], rho)        int64   [nz*nx*5] or NULL
+ *   has_stif the reference's "stif_den is not None" as seen by the jitted code (the
+ *            class substitutes zeros for None, ATR:3890-3891, so it is normally 1)
+ *   group_vel / phase_vel  velocity tables        float64 [361*n_cols], column 0 = angle */
+typedef struct {
+    int32_t nz, nx;
+    double dnx;
+    const double *veln;
+    const int32_t *velpn;
+    const double *vel_map;
+    const int64_t *stif_den;
+    int32_t has_stif;
+    const double *group_vel;
+    const double *phase_vel;
+    int32_t n_cols;
+} alifmm_model_desc;
+
+typedef struct {
+    int64_t node_solves;      /* final travel times produced (nodes x sources) */
+    int64_t seq_pops;         /* nodes accepted by the sequential near-source replica */
+    int64_t seq_evals;        /* ALI update evaluations in the sequential replica */
+    int64_t band_rounds;      /* sum over sources of band-march rounds */
+    int64_t band_rounds_max;  /* slowest source */
+    int64_t band_evals;       /* ALI update evaluations in the band march */
+    int64_t fallback_evals;   /* fouds18_A fallback evaluations (ATR:240) */
+    int64_t max_band;         /* largest narrow band seen */
+    int64_t rays;             /* rays traced by the last alifmm_rays call */
+    int64_t ray_points;       /* path points written by the last alifmm_rays call */
+    int64_t kernel_launches;  /* kernels launched by the last ttf / rays call */
+    double ms_seq;            /* device time of the last call's kernels (CUDA events) */
+    double ms_march;
+    double ms_finalize;
+    double ms_rays;
+    double vmax;              /* model-wide phase-velocity bound used for delta */
+    double delta;             /* acceptance band of the last field batch, seconds */
+} alifmm_counters_t;
+
+/* Number of CUDA devices visible to the process (0 when there is none). */
+int alifmm_device_count(void);
+
+/* Uploads the model to `device` and keeps it resident.  Replaces the model hand-over
+ * of ALI_FMM.update / update_i / find_all_TTF_rays (ATR:3889-3900, 4073-4076). */
+int alifmm_create(const alifmm_model_desc *desc, int device, alifmm_ctx **out);
+void alifmm_destroy(alifmm_ctx *ctx);
+
+/* Options: "delta_frac" (acceptance band as a fraction of dnx/vmax, default 0.25, must
+ * be <= 0.4), "handover_margin" (nodes the sequential replica runs past the last
+ * refined source box, default 27), "band_capacity_factor" (narrow-band list capacity as
+ * a multiple of nz+nx of the solved grid, default 6), "threads_per_source" (CTA size of
+ * the band march, default 1024). */
+int alifmm_set_option(alifmm_ctx *ctx, const char *name, double value);
+
+/* Runs the library's kernels on the caller's CUDA stream (a cudaStream_t passed as
+ * void*); NULL restores the context's own stream. */
+int alifmm_set_stream(alifmm_ctx *ctx, void *cuda_stream);
+
+/* Travel-time fields of n_src sources at once.  Source k sits on coarse node
+ * (src_iz[k], src_ix[k]) (the reference rounds scx/dnx, scz/dnx: ATR:1509-1510).
+ * subgrid == 1 replaces travel() (ATR:1463); odd subgrid > 1 replaces
+ * travel_finer_grid() (ATR:2120) and returns fields of (subgrid*(nz-1)+1) x
+ * (subgrid*(nx-1)+1) nodes.  The fields stay resident on the device as slots
+ * 0..n_src-1 until the next call; out_host (n_src fields back to back) may be NULL. */
+int alifmm_ttf(alifmm_ctx *ctx, int32_t n_src, const int32_t *src_iz, const int32_t *src_ix, int32_t subgrid,
+               double *out_host);
+
+/* Copies one resident field to the host. */
+int alifmm_ttf_fetch(alifmm_ctx *ctx, int32_t slot, double *out_host);
+
+/* Extents of the resident fields. */
+int alifmm_ttf_shape(alifmm_ctx *ctx, int32_t *n_slots, int32_t *fz, int32_t *fx, int32_t *subgrid);
+
+/* Traces n_rays rays through resident fields; replaces find_ray() (ATR:3104) as called
+ * from find_all_TTF_rays (ATR:4349) / parallel_TTF_rays (ATR:3728).  Ray r starts on
+ * coarse node (src_iz[r], src_ix[r]) and runs to the source node of field rec_slot[r].
+ * Outputs, per ray: out_x / out_y [capacity] path points in FINE-grid units (the caller
+ * divides by subgrid, ATR:3729-3730), out_len, out_time (seconds), out_flag (bit 0: the
+ * reference's "Travel time to receiver increasing" early exit, bit 1: plane left the
+ * grid, bit 2: empty plane, bit 3: capacity reached).  capacity is the reference's
+ * 5*(nz+nx) unless the caller wants less. */
+int alifmm_rays(alifmm_ctx *ctx, int32_t n_rays, const int32_t *src_iz, const int32_t *src_ix,
+                const int32_t *rec_slot, int32_t capacity, double *out_x, double *out_y, int32_t *out_len,
+                double *out_time, int32_t *out_flag);
+
+/* Free / total bytes of the context's device (used by the host side to size batches). */
+int alifmm_mem_info(alifmm_ctx *ctx, int64_t *free_bytes, int64_t *total_bytes);
+
+/* Work counters and device timings of the last calls (feeds bench.py's roofline). */
+int alifmm_counters(alifmm_ctx *ctx, alifmm_counters_t *out);
+
+/* Christoffel curves of one material, 361 samples at 1 degree; replaces
+ * ALI_FMM.generate_group_vel / generate_phase_vel (ATR:4112-4206).  Stiffness in Pa. */
+int alifmm_velocity_curves(alifmm_ctx *ctx, double c22, double c23, double c33, double c44, double density,
+                           double *group_out, double *phase_out);
+
+/* Model sanity scan; replaces min_max_vel (ATR:3736-3787). */
+int alifmm_min_max_vel(alifmm_ctx *ctx, double *min_vel, double *max_vel);
+
+const char *alifmm_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ALIFMM_H */
