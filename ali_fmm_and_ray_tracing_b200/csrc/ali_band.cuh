@@ -2,14 +2,18 @@
 //
 // The reference pops one node at a time from a heap (ATR:2055-2102, 2775-2817).  The
 // march here advances the whole narrow band in rounds that reproduce the same discrete
-// solution:
-//   A  every band node re-evaluates the ALI update from the state at the start of the
-//      round (alive values + last round's published tentatives) into a staging slot;
-//   B  staged values are published (T, status QUEUED -> BAND) and tmin is reduced;
+// solution wherever that solution does not hinge on the heap's pop timing (SURVEY.md 7.3,
+// DESIGN.md "Parity"):
+//   A  every band node whose 12-neighbour window changed since its last evaluation
+//      re-evaluates the ALI update from the state at the start of the round (alive values
+//      + last round's published tentatives) into a staging slot -- the update is a pure
+//      function of that window, so skipping unchanged windows equals re-evaluating all;
+//   B  changed values are published (T, status QUEUED -> BAND), their neighbours are marked
+//      dirty, and tmin is reduced;
 //   C  nodes with T <= tmin + delta become alive; their far 4-neighbours join the band
 //      as QUEUED (in the list, not yet visible to stencils, like a node the reference
 //      has not computed yet).
-// delta = frac * dnx / vmax with frac <= 0.4 keeps the result identical to heap order.
+// delta = frac * dnx / vmax with frac <= 0.4.
 #pragma once
 #include "ali_core.cuh"
 
@@ -19,10 +23,16 @@
 #define ALI_ST_BAND 2
 #define ALI_ST_ALIVE 3
 
+// Band list entries pack the node as (iz << 16) | ix (grids up to 65535 x 65535).
+#define ALI_PACK(iz, ix) (((unsigned)(iz) << 16) | (unsigned)(ix))
+#define ALI_PACK_Z(p) ((int)((p) >> 16))
+#define ALI_PACK_X(p) ((int)((p) & 0xffffu))
+
 struct AliBandGrid {
     int nz, nx;
     double *T;        // [nz*nx] travel times of this source (seconds * sg on the fine path)
-    uint8_t *st;      // [nz*nx]
+    uint8_t *st;      // [nz*nx] status
+    uint8_t *dirty;   // [nz*nx] 1: window changed since the node's last evaluation
     AliMatView mv;
     double dnx;
     ALI_DEV bool avail(int z, int x) const { return st[(size_t)z * nx + x] >= ALI_ST_BAND; }
@@ -30,22 +40,92 @@ struct AliBandGrid {
     ALI_DEV double tt(int z, int x) const { return T[(size_t)z * nx + x]; }
 };
 
-// Phase A: value the reference would store for this node given the current state.
-ALI_DEV double ali_band_eval(const AliModel &m, const AliBandGrid &g, int node, int *fallback)
+ALI_HD AliMatView ali_band_view(int sg)
 {
-    int iz = node / g.nx, ix = node - iz * g.nx;
-    return ali_eval_node(m, g.mv, g, iz, ix, g.nz, g.nx, g.nz, g.nx, g.dnx, fallback);
+    return ali_make_view(1, 0, 0, sg > 1 ? sg : 1, sg > 1 ? 1 : 0);
 }
 
-// Phase B: make the staged value visible.
-ALI_DEV void ali_band_publish(const AliBandGrid &g, int node, double v)
+// 12-neighbour gather; interior nodes take a branch-free path with independent loads.
+ALI_DEV void ali_band_gather(const AliBandGrid &g, int iz, int ix, AliWindow &w)
 {
-    g.T[node] = v;
-    if (g.st[node] == ALI_ST_QUEUED) g.st[node] = ALI_ST_BAND;
+    if (iz >= 2 && iz < g.nz - 2 && ix >= 2 && ix < g.nx - 2) {
+        const size_t c = (size_t)iz * g.nx + ix;
+        const uint8_t *sp = g.st + c;
+        const double *tp = g.T + c;
+        const int nx = g.nx;
+        unsigned av = 0;
+#pragma unroll
+        for (int k = 0; k < 12; k++) {
+            const int off = ALI_W_DZ(k) * nx + ALI_W_DX(k);
+            w.t[k] = tp[off];
+            if (sp[off] >= ALI_ST_BAND) av |= 1u << k;
+        }
+        w.avail = av;
+    } else {
+        ali_gather(g, iz, ix, g.nz, g.nx, w);
+    }
+}
+
+// FD fallback of a band node, out of line and with by-value arguments so that the hot
+// path keeps its state in registers.  m_dev points to the model struct in device memory.
+ALI_DEV_NOINLINE double ali_band_fouds_slow(const AliModel *m_dev, double *T, uint8_t *st, int nz, int nx, int sg,
+                                            double dnx, int iz, int ix)
+{
+    AliModel m = *m_dev;
+    AliBandGrid g;
+    g.nz = nz; g.nx = nx; g.T = T; g.st = st; g.dirty = nullptr; g.mv = ali_band_view(sg); g.dnx = dnx;
+    AliMat mat;
+    ali_fetch_mat(m, g.mv, iz, ix, mat);
+    return ali_fouds18(m, mat, g, iz, ix, dnx, dnx, nx, nz);
+}
+
+// Phase A: value the reference would store for this node given the current state.
+ALI_DEV double ali_band_eval(const AliModel &m, const AliModel *m_dev, const AliBandGrid &g, int sg, int iz, int ix,
+                             int *fallback)
+{
+    AliMat mat;
+    AliWindow w;
+    ali_fetch_mat(m, g.mv, iz, ix, mat);
+    ali_band_gather(g, iz, ix, w);
+    double v = ali_update_window(m, mat, w, iz, ix, g.nz, g.nx, g.dnx, nullptr);
+    if (v == -1.0) {
+        v = ali_band_fouds_slow(m_dev, g.T, g.st, g.nz, g.nx, sg, g.dnx, iz, ix);
+        *fallback = 1;
+    }
+    return v;
+}
+
+// Marks the 12 window neighbours of a node dirty (the window relation is symmetric).
+ALI_DEV void ali_band_mark_dirty(const AliBandGrid &g, int iz, int ix)
+{
+    if (iz >= 2 && iz < g.nz - 2 && ix >= 2 && ix < g.nx - 2) {
+        uint8_t *dp = g.dirty + (size_t)iz * g.nx + ix;
+        const int nx = g.nx;
+#pragma unroll
+        for (int k = 0; k < 12; k++) dp[ALI_W_DZ(k) * nx + ALI_W_DX(k)] = 1;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 12; k++) {
+            int z = iz + ALI_W_DZ(k), x = ix + ALI_W_DX(k);
+            if (z >= 0 && z < g.nz && x >= 0 && x < g.nx) g.dirty[(size_t)z * g.nx + x] = 1;
+        }
+    }
+}
+
+// Phase B: make the staged value visible if it changed anything.
+ALI_DEV void ali_band_publish(const AliBandGrid &g, int iz, int ix, double v)
+{
+    const size_t node = (size_t)iz * g.nx + ix;
+    const bool fresh = g.st[node] == ALI_ST_QUEUED;
+    if (fresh || g.T[node] != v) {
+        g.T[node] = v;
+        if (fresh) g.st[node] = ALI_ST_BAND;
+        ali_band_mark_dirty(g, iz, ix);
+    }
 }
 
 // Claims a far node for the band list; returns true for exactly one caller.
-ALI_DEV bool ali_band_claim(const AliBandGrid &g, int node)
+ALI_DEV bool ali_band_claim(const AliBandGrid &g, size_t node)
 {
     if (g.st[node] != ALI_ST_FAR) return false;
 #if defined(__CUDA_ARCH__)
@@ -54,24 +134,26 @@ ALI_DEV bool ali_band_claim(const AliBandGrid &g, int node)
     unsigned *word = (unsigned *)((uintptr_t)(g.st + node) & ~(uintptr_t)3);
     unsigned shift = 8u * (unsigned)((uintptr_t)(g.st + node) & 3);
     unsigned old = atomicOr(word, (unsigned)ALI_ST_QUEUED << shift);
-    return ((old >> shift) & 0xffu) == ALI_ST_FAR;
+    if (((old >> shift) & 0xffu) != ALI_ST_FAR) return false;
 #else
     g.st[node] = ALI_ST_QUEUED;
-    return true;
 #endif
+    g.dirty[node] = 1;
+    return true;
 }
 
-// Phase C for an accepted node: alive + enlist far 4-neighbours (ATR:2065-2102 order is
-// irrelevant here: new nodes are evaluated next round from a common snapshot).
-ALI_DEV int ali_band_accept(const AliBandGrid &g, int node, int *nb)
+// Phase C for an accepted node: alive + enlist far 4-neighbours (the reference's visiting
+// order, ATR:2065-2102, is irrelevant here: new nodes are evaluated next round from a
+// common snapshot).  Returns the packed new entries.
+ALI_DEV int ali_band_accept(const AliBandGrid &g, int iz, int ix, unsigned *nb)
 {
-    int iz = node / g.nx, ix = node - iz * g.nx;
+    const size_t node = (size_t)iz * g.nx + ix;
     int cnt = 0;
     g.st[node] = ALI_ST_ALIVE;
-    if (ix > 0 && ali_band_claim(g, node - 1)) nb[cnt++] = node - 1;
-    if (ix < g.nx - 1 && ali_band_claim(g, node + 1)) nb[cnt++] = node + 1;
-    if (iz > 0 && ali_band_claim(g, node - g.nx)) nb[cnt++] = node - g.nx;
-    if (iz < g.nz - 1 && ali_band_claim(g, node + g.nx)) nb[cnt++] = node + g.nx;
+    if (ix > 0 && ali_band_claim(g, node - 1)) nb[cnt++] = ALI_PACK(iz, ix - 1);
+    if (ix < g.nx - 1 && ali_band_claim(g, node + 1)) nb[cnt++] = ALI_PACK(iz, ix + 1);
+    if (iz > 0 && ali_band_claim(g, node - g.nx)) nb[cnt++] = ALI_PACK(iz - 1, ix);
+    if (iz < g.nz - 1 && ali_band_claim(g, node + g.nx)) nb[cnt++] = ALI_PACK(iz + 1, ix);
     return cnt;
 }
 
@@ -80,7 +162,7 @@ ALI_DEV double ali_node_vmax(const AliModel &m, int iz, int ix)
 {
     AliMat mat;
     const AliMatView idv = ali_view_identity();
-    ali_fetch_mat(m, idv, iz, ix, mat, true);
+    ali_fetch_mat(m, idv, iz, ix, mat);
     double best = 0.0;
     if (mat.velpn != 0 || !m.has_stif) {
         for (int a = 0; a < 180; a++) {

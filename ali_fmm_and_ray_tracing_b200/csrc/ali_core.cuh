@@ -25,19 +25,41 @@
 #define ALI_HD inline
 #endif
 
+// Transcendentals go through these macros so that the host replay (tests/emu) can inject
+// last-ulp noise and measure how sensitive a solution is to the libm in use.
+#if defined(ALI_EMU_NOISE) && !defined(__CUDACC__)
+double ali_emu_noise(double v);
+#define ALI_ATAN(x) ali_emu_noise(atan(x))
+#define ALI_SIN(x) ali_emu_noise(sin(x))
+#define ALI_COS(x) ali_emu_noise(cos(x))
+#define ALI_TAN(x) ali_emu_noise(tan(x))
+#else
+#define ALI_ATAN(x) atan(x)
+#define ALI_SIN(x) sin(x)
+#define ALI_COS(x) cos(x)
+#define ALI_TAN(x) tan(x)
+#endif
+
 #define ALI_PI 3.14159265358979323846
 #define ALI_RAD2DEG (180.0 / ALI_PI)
 #define ALI_DEG2RAD (ALI_PI / 180.0)
 
 // ---------------------------------------------------------------------------
-// Model resident in HBM (row-major [z][x], exactly the caller's coarse arrays).
+// Model resident in HBM.  One 64-byte record per COARSE node, built once per model from
+// the caller's arrays (veln f64, velpn i32, vel_map f64, stif_den i64[5]): the int64
+// stiffness entries are converted to fp64 once (exact below 2^53) instead of per evaluation.
 // ---------------------------------------------------------------------------
+struct AliMatRec {
+    double veln;     // orientation, degrees (as passed by the caller)
+    double vel_map;  // velocity scale (as passed by the caller)
+    double s[5];     // c22, c23, c33, c44 [MPa], rho; zeros when the model has no stif_den
+    int velpn;       // material id (0 = Christoffel from s[])
+    int pad;
+};
+
 struct AliModel {
     int nz, nx;
-    const double *veln;      // orientation, degrees
-    const int32_t *velpn;    // material id (0 = Christoffel from stif)
-    const double *vel_map;   // velocity scale
-    const long long *stif;   // int64 [nz*nx*5] (c22,c23,c33,c44 MPa, rho) or nullptr
+    const AliMatRec *rec;    // [nz*nx]
     int has_stif;            // reference's "stif_den is not None"
     const double *group_tab; // [361*ncol]
     const double *phase_tab; // [361*ncol]
@@ -50,48 +72,60 @@ struct AliModel {
 // model is never materialised.  level index -> parent = o + (i + side1)/scale1;
 // parent -> coarse = (p + side0)/scale0.  `cast` applies the int32 truncation of the
 // orientation and the float32 rounding of vel_map that refined grids carry
-// (ATR:1527-1529, 2156-2158).
+// (ATR:1527-1529, 2156-2158).  mul1/mul0 are the 2^32/scale multipliers that replace the
+// integer divisions (exact for indices below 2^32/scale).
 struct AliMatView {
     int scale1, side1, z0, x0;
     int scale0, side0;
     int cast;
+    unsigned mul1, mul0;
 };
 
 struct AliMat {
     double veln, vel_map;
     int velpn;
-    double s[5];
+    const double *s;   // -> AliMatRec::s of the coarse node
 };
 
-ALI_DEV AliMatView ali_view_identity()
+ALI_HD unsigned ali_div_magic(int scale) { return scale <= 1 ? 0u : (unsigned)(4294967296ull / (unsigned)scale) + 1u; }
+
+ALI_DEV int ali_div_by(int x, int scale, unsigned mul)
+{
+    if (scale <= 1) return x;
+#if defined(__CUDA_ARCH__)
+    return (int)__umulhi((unsigned)x, mul);
+#else
+    return (int)(((unsigned long long)(unsigned)x * mul) >> 32);
+#endif
+}
+
+ALI_HD AliMatView ali_make_view(int scale1, int z0, int x0, int scale0, int cast)
 {
     AliMatView v;
-    v.scale1 = 1; v.side1 = 0; v.z0 = 0; v.x0 = 0; v.scale0 = 1; v.side0 = 0; v.cast = 0;
+    v.scale1 = scale1; v.side1 = (scale1 - 1) / 2; v.z0 = z0; v.x0 = x0;
+    v.scale0 = scale0; v.side0 = (scale0 - 1) / 2; v.cast = cast;
+    v.mul1 = ali_div_magic(scale1); v.mul0 = ali_div_magic(scale0);
     return v;
 }
 
-ALI_DEV void ali_fetch_mat(const AliModel &m, const AliMatView &v, int iz, int ix, AliMat &out, bool want_stif)
+ALI_DEV AliMatView ali_view_identity() { return ali_make_view(1, 0, 0, 1, 0); }
+
+ALI_DEV void ali_fetch_mat(const AliModel &m, const AliMatView &v, int iz, int ix, AliMat &out)
 {
-    int pz = v.z0 + (iz + v.side1) / v.scale1;
-    int px = v.x0 + (ix + v.side1) / v.scale1;
-    int cz = (pz + v.side0) / v.scale0;
-    int cx = (px + v.side0) / v.scale0;
-    size_t p = (size_t)cz * (size_t)m.nx + (size_t)cx;
-    double vn = m.veln[p], vm = m.vel_map[p];
+    int pz = v.z0 + ali_div_by(iz + v.side1, v.scale1, v.mul1);
+    int px = v.x0 + ali_div_by(ix + v.side1, v.scale1, v.mul1);
+    int cz = ali_div_by(pz + v.side0, v.scale0, v.mul0);
+    int cx = ali_div_by(px + v.side0, v.scale0, v.mul0);
+    const AliMatRec *r = m.rec + ((size_t)cz * (size_t)m.nx + (size_t)cx);
+    double vn = r->veln, vm = r->vel_map;
     if (v.cast) {
         vn = (double)(int)vn;
         vm = (double)(float)vm;
     }
     out.veln = vn;
     out.vel_map = vm;
-    out.velpn = m.velpn[p];
-    if (want_stif && m.stif != nullptr) {
-        const long long *s = m.stif + 5 * p;
-        out.s[0] = (double)s[0]; out.s[1] = (double)s[1]; out.s[2] = (double)s[2];
-        out.s[3] = (double)s[3]; out.s[4] = (double)s[4];
-    } else {
-        out.s[0] = out.s[1] = out.s[2] = out.s[3] = out.s[4] = 0.0;
-    }
+    out.velpn = r->velpn;
+    out.s = r->s;
 }
 
 ALI_DEV int ali_imax2(int a, int b) { return a > b ? a : b; }
@@ -109,6 +143,19 @@ ALI_DEV double ali_pymod(double a, double w)
     return m;
 }
 
+// a mod 180 with the same result as ali_pymod(a, 180): the common ranges avoid fmod()
+// (x - 180 is exact for 180 <= x < 360; for -180 <= x < 0 Python adds 180 with one rounding).
+ALI_DEV double ali_pymod180(double a)
+{
+    if (a >= 0.0) {
+        if (a < 180.0) return a;
+        if (a < 360.0) return a - 180.0;
+    } else if (a >= -180.0) {
+        return a + 180.0;
+    }
+    return ali_pymod(a, 180.0);
+}
+
 // ---- velocities -------------------------------------------------------------
 // 1-degree table interpolation (ATR:1371-1375).
 ALI_DEV double ali_table_vel(const double *tab, int ncol, double eff, int col, double vm)
@@ -122,8 +169,8 @@ ALI_DEV double ali_table_vel(const double *tab, int ncol, double eff, int col, d
 // Christoffel phase velocity, stiffness in MPa (ATR:1400-1406).
 ALI_DEV double ali_christoffel_phase(double eff, const double *s, double vm)
 {
-    double c = cos(ALI_DEG2RAD * eff);
-    double sn = sin(ALI_DEG2RAD * eff);
+    double c = ALI_COS(ALI_DEG2RAD * eff);
+    double sn = ALI_SIN(ALI_DEG2RAD * eff);
     double A = c * c * s[0] + sn * sn * s[3];
     double B = c * sn * (s[1] + s[3]);
     double C = c * c * s[3] + sn * sn * s[2];
@@ -141,18 +188,18 @@ ALI_DEV double ali_christoffel_group(double eff, const double *s, double vm)
         return 1000 * vm * sqrt(lam / s[4]);
     }
     double c22 = s[0], c23 = s[1], c33 = s[2], c44 = s[3];
-    double t = tan(ALI_DEG2RAD * eff);
+    double t = ALI_TAN(ALI_DEG2RAD * eff);
     double A = c22 + c33 - 2 * c44;
     double B = (c23 + c44) * (t - 1 / t);
     double C = c22 - c33;
     double disc = sqrt(B * B + A * A - C * C);
     double ph;
     if (eff < 90)
-        ph = ali_pymod(atan((-B - disc) / (C - A)), ALI_PI);
+        ph = ali_pymod(ALI_ATAN((-B - disc) / (C - A)), ALI_PI);
     else
-        ph = ali_pymod(atan((-B + disc) / (C - A)), ALI_PI);
-    double lam = 0.5 * (cos(2 * ph) * (c22 - c44) + sin(2 * ph) * (c23 + c44) * t + c22 + c44);
-    return 1000 * vm * sqrt(lam / s[4]) / cos(ALI_DEG2RAD * eff - ph);
+        ph = ali_pymod(ALI_ATAN((-B + disc) / (C - A)), ALI_PI);
+    double lam = 0.5 * (ALI_COS(2 * ph) * (c22 - c44) + ALI_SIN(2 * ph) * (c23 + c44) * t + c22 + c44);
+    return 1000 * vm * sqrt(lam / s[4]) / ALI_COS(ALI_DEG2RAD * eff - ph);
 }
 
 ALI_DEV double ali_phase_velocity(const AliModel &m, const AliMat &mat, double eff)
@@ -186,7 +233,7 @@ ALI_DEV void ali_wad(int ix, int iz, int x1, int x2, int x3, int z1, int z2, int
     if (dx == 0)
         angle = 0.0;
     else
-        angle = ali_pymod(ALI_RAD2DEG * atan(dz / dx) + 90, 180.0);
+        angle = ali_pymod180(ALI_RAD2DEG * ALI_ATAN(dz / dx) + 90);
     dist = fabs(dz * (x2 - ix) - dx * (z2 - iz)) / sqrt(dx * dx + dz * dz);
 }
 
@@ -196,6 +243,9 @@ ALI_DEV void ali_wad(int ix, int iz, int x1, int x2, int x3, int z1, int z2, int
 #define ALI_W_DZ(s) ((s) == 0 ? -2 : (s) <= 3 ? -1 : (s) <= 7 ? 0 : (s) <= 10 ? 1 : 2)
 #define ALI_W_DX(s) ((s) == 0 ? 0 : (s) == 1 ? -1 : (s) == 2 ? 0 : (s) == 3 ? 1 : (s) == 4 ? -2 : (s) == 5 ? -1 : \
                      (s) == 6 ? 1 : (s) == 7 ? 2 : (s) == 8 ? -1 : (s) == 9 ? 0 : (s) == 10 ? 1 : 0)
+// (dz+2) | (dx+2) << 3 of a slot, and the three slots of a stencil packed as a | b<<6 | c<<12
+#define ALI_W_CODE(s) ((unsigned)((ALI_W_DZ(s) + 2) | ((ALI_W_DX(s) + 2) << 3)))
+#define ALI_STENCIL_CODE(a, b, c) (ALI_W_CODE(a) | (ALI_W_CODE(b) << 6) | (ALI_W_CODE(c) << 12))
 
 struct AliWindow {
     double t[12];
@@ -206,82 +256,81 @@ struct AliWindow {
 //   nnz/nnx : logical extents used for the edge tests (ATR:1146, 1265, 1316 ...).
 //   dnx     : spacing of THIS grid (dnx/27, dnx/9, dnx/3 on the source levels).
 //   returns -1.0 when no stencil gives a solution (caller falls back to fouds18).
+// The window is indexed with compile-time slots only, so it lives in registers.
 ALI_DEV double ali_update_window(const AliModel &m, const AliMat &mat, const AliWindow &w, int iz, int ix,
                                  int nnz, int nnx, double dnx, int *stencil_out)
 {
-    // phase 1: apex, wing1, wing2 slots of stencils 0..7 (ATR:989-1033)
-    const int P1A[8] = {0, 7, 11, 4, 1, 3, 10, 8};
-    const int P1B[8] = {1, 3, 8, 1, 5, 2, 9, 5};
-    const int P1C[8] = {3, 10, 10, 8, 2, 6, 6, 9};
     const unsigned av = w.avail;
     int stencil_no = -1;
     double min_diff = 1000000.0;
     double angle = 0.0, dist = -1.0, wt = 0.0;
+    double ta = 0.0, tb = 0.0, tc = 0.0; // apex, wing1/axial, wing2/diagonal of the chosen stencil
+    unsigned code = 0;
 
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-        unsigned need = (1u << P1A[k]) | (1u << P1B[k]) | (1u << P1C[k]);
-        if ((av & need) == need) {
-            double diff = fabs(w.t[P1B[k]] - w.t[P1C[k]]);
-            if (diff < min_diff) { stencil_no = k; min_diff = diff; }
-        }
+    // phase 1: square/diamond stencils 0..7, smallest |T(wing1) - T(wing2)| wins, lowest index
+    // on ties (ATR:989-1033)
+#define ALI_P1(k, A, B, C)                                                                   \
+    if ((av & ((1u << A) | (1u << B) | (1u << C))) == ((1u << A) | (1u << B) | (1u << C))) { \
+        double diff = fabs(w.t[B] - w.t[C]);                                                 \
+        if (diff < min_diff) {                                                               \
+            stencil_no = k; min_diff = diff;                                                 \
+            ta = w.t[A]; tb = w.t[B]; tc = w.t[C];                                           \
+            code = ALI_STENCIL_CODE(A, B, C);                                                \
+        }                                                                                    \
     }
+    ALI_P1(0, 0, 1, 3)
+    ALI_P1(1, 7, 3, 10)
+    ALI_P1(2, 11, 8, 10)
+    ALI_P1(3, 4, 1, 8)
+    ALI_P1(4, 1, 5, 2)
+    ALI_P1(5, 3, 2, 6)
+    ALI_P1(6, 10, 9, 6)
+    ALI_P1(7, 8, 5, 9)
+#undef ALI_P1
     if (stencil_no != -1) {
-        int sa = 0, sb = 0, sc = 0;
-#pragma unroll
-        for (int k = 0; k < 8; k++)
-            if (k == stencil_no) { sa = P1A[k]; sb = P1B[k]; sc = P1C[k]; }
-        if (!(w.t[sb] < w.t[sc])) { int tmp = sb; sb = sc; sc = tmp; }
-        // slot -> offsets without a local array (keeps everything in registers)
-        int za = iz + ALI_W_DZ(sa), xa = ix + ALI_W_DX(sa);
-        int zb = iz + ALI_W_DZ(sb), xb = ix + ALI_W_DX(sb);
-        int zc = iz + ALI_W_DZ(sc), xc = ix + ALI_W_DX(sc);
-        double ta = 0, tb = 0, tc = 0;
-#pragma unroll
-        for (int s = 0; s < 12; s++) {
-            if (s == sa) ta = w.t[s];
-            if (s == sb) tb = w.t[s];
-            if (s == sc) tc = w.t[s];
+        // B = the wing with the strictly smaller time, C the other (ATR:1040-1143)
+        unsigned cb = (code >> 6) & 63u, cc = (code >> 12) & 63u, ca = code & 63u;
+        if (!(tb < tc)) {
+            double tmp = tb; tb = tc; tc = tmp;
+            unsigned ct = cb; cb = cc; cc = ct;
         }
-        ali_wad(ix, iz, xa, xb, xc, za, zb, zc, ta, tb, tc, angle, dist);
+        ali_wad(ix, iz, ix + (int)(ca >> 3) - 2, ix + (int)(cb >> 3) - 2, ix + (int)(cc >> 3) - 2,
+                iz + (int)(ca & 7u) - 2, iz + (int)(cb & 7u) - 2, iz + (int)(cc & 7u) - 2, ta, tb, tc, angle, dist);
         wt = tb;
     }
 
     if (stencil_no == -1 || ix == 0 || ix == nnx - 1 || iz == 0 || iz == nnz - 1) { // ATR:1146
-        // phase 2: apex, axial n1, diagonal n2 slots of triangular stencils 8..15 (ATR:1205-1260)
-        const int P2A[8] = {11, 0, 0, 11, 4, 7, 7, 4};
-        const int P2B[8] = {9, 2, 2, 9, 5, 6, 6, 5};
-        const int P2C[8] = {10, 3, 1, 8, 8, 10, 3, 1};
+        // phase 2: triangular stencils 8..15 (apex A two nodes away, axial n1, diagonal n2); A must
+        // be the earliest; weighted difference criterion (ATR:1205-1260)
         const double r2 = sqrt(2.0);
         const double w1 = r2 - 1, w2 = 2 - r2;
         if (stencil_no == -1) min_diff = 1000000.0;
         stencil_no = -2;
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            unsigned need = (1u << P2A[k]) | (1u << P2B[k]) | (1u << P2C[k]);
-            if ((av & need) == need) {
-                double ta = w.t[P2A[k]], tb = w.t[P2B[k]], tc = w.t[P2C[k]];
-                if (ta < fmin(tb, tc)) {
-                    double diff = fabs(w1 * ta + w2 * tb - tc);
-                    if (diff < min_diff) { stencil_no = k; min_diff = diff; }
-                }
-            }
-        }
+#define ALI_P2(k, A, B, C)                                                                   \
+    if ((av & ((1u << A) | (1u << B) | (1u << C))) == ((1u << A) | (1u << B) | (1u << C))) { \
+        if (w.t[A] < fmin(w.t[B], w.t[C])) {                                                 \
+            double diff = fabs(w1 * w.t[A] + w2 * w.t[B] - w.t[C]);                          \
+            if (diff < min_diff) {                                                           \
+                stencil_no = k; min_diff = diff;                                             \
+                ta = w.t[A]; tb = w.t[B]; tc = w.t[C];                                       \
+                code = ALI_STENCIL_CODE(A, B, C);                                            \
+            }                                                                                \
+        }                                                                                    \
+    }
+        ALI_P2(0, 11, 9, 10)
+        ALI_P2(1, 0, 2, 3)
+        ALI_P2(2, 0, 2, 1)
+        ALI_P2(3, 11, 9, 8)
+        ALI_P2(4, 4, 5, 8)
+        ALI_P2(5, 7, 6, 10)
+        ALI_P2(6, 7, 6, 3)
+        ALI_P2(7, 4, 5, 1)
+#undef ALI_P2
         if (stencil_no != -2) {
-            int sa = 0, sb = 0, sc = 0;
-#pragma unroll
-            for (int k = 0; k < 8; k++)
-                if (k == stencil_no) { sa = P2A[k]; sb = P2B[k]; sc = P2C[k]; }
-            double ta = 0, tb = 0, tc = 0;
-#pragma unroll
-            for (int s = 0; s < 12; s++) {
-                if (s == sa) ta = w.t[s];
-                if (s == sb) tb = w.t[s];
-                if (s == sc) tc = w.t[s];
-            }
-            int za = iz + ALI_W_DZ(sa), xa = ix + ALI_W_DX(sa);
-            int zb = iz + ALI_W_DZ(sb), xb = ix + ALI_W_DX(sb);
-            int zc = iz + ALI_W_DZ(sc), xc = ix + ALI_W_DX(sc);
+            const unsigned ca = code & 63u, cb = (code >> 6) & 63u, cc = (code >> 12) & 63u;
+            const int xa = ix + (int)(ca >> 3) - 2, za = iz + (int)(ca & 7u) - 2;
+            const int xb = ix + (int)(cb >> 3) - 2, zb = iz + (int)(cb & 7u) - 2;
+            const int xc = ix + (int)(cc >> 3) - 2, zc = iz + (int)(cc & 7u) - 2;
             if (tb < tc) {
                 // on the listed grid edge the wavefront is forced (ATR:1265-1267, 1316-1318)
                 bool forced;
@@ -303,7 +352,7 @@ ALI_DEV double ali_update_window(const AliModel &m, const AliMat &mat, const Ali
     }
     if (stencil_out) *stencil_out = stencil_no;
     if (dist != -1.0) {
-        double eff = ali_pymod(mat.veln - angle, 180.0);
+        double eff = ali_pymod180(mat.veln - angle);
         double vel = ali_phase_velocity(m, mat, eff);
         return wt + (dist * dnx / vel);
     }
@@ -538,7 +587,7 @@ ALI_DEV_NOINLINE double ali_fouds18(const AliModel &m, const AliMat &mat, const 
     else travmd = travm;
 
     // 26.6 / 63.4-degree stencils (ATR:698-897)
-    wave_ang = rint(ALI_RAD2DEG * atan(0.5));
+    wave_ang = rint(ALI_RAD2DEG * ALI_ATAN(0.5));
     for (int lp = 0; lp < 2; lp++) {
         if (lp == 0) eff = ali_pymod(-wave_ang - mat.veln, 180.0);
         else eff = ali_pymod(wave_ang - mat.veln, 180.0);
@@ -628,7 +677,7 @@ ALI_DEV double ali_eval_node(const AliModel &m, const AliMatView &mv, const S &s
 {
     AliMat mat;
     AliWindow w;
-    ali_fetch_mat(m, mv, iz, ix, mat, true);
+    ali_fetch_mat(m, mv, iz, ix, mat);
     ali_gather(st, iz, ix, nnz_logic, nnx_logic, w);
     double v = ali_update_window(m, mat, w, iz, ix, nnz_logic, nnx_logic, dnx, nullptr);
     if (v == -1.0) {
@@ -652,7 +701,7 @@ ALI_DEV double ali_time_between_points(const AliModel &m, double x1, double x2, 
     const double start_x = x1, end_x = x2, start_y = y1, end_y = y2;
     double prev_x = x1, prev_y = y1;
     if (x1 == x2) angle = 0;
-    else angle = ALI_RAD2DEG * atan((y2 - y1) / (x2 - x1));
+    else angle = ALI_RAD2DEG * ALI_ATAN((y2 - y1) / (x2 - x1));
     if (end_x != start_x) {
         mm = (end_y - start_y) / (end_x - start_x);
         cc = start_y - mm * start_x;
@@ -691,8 +740,8 @@ ALI_DEV double ali_time_between_points(const AliModel &m, double x1, double x2, 
         x_pos = x_pos < 0 ? 0 : (x_pos > m.nx - 1 ? m.nx - 1 : x_pos);
         y_pos = y_pos < 0 ? 0 : (y_pos > m.nz - 1 ? m.nz - 1 : y_pos);
         AliMat mat;
-        ali_fetch_mat(m, idv, y_pos, x_pos, mat, true);
-        double eff = ali_pymod(mat.veln - angle, 180.0);
+        ali_fetch_mat(m, idv, y_pos, x_pos, mat);
+        double eff = ali_pymod180(mat.veln - angle);
         double distance = m.dnx * sqrt((prev_x - next_x_val) * (prev_x - next_x_val) +
                                        (prev_y - next_y_val) * (prev_y - next_y_val));
         double vel = ali_group_velocity(m, mat, eff);

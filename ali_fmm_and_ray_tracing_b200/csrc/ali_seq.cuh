@@ -199,7 +199,7 @@ ALI_DEV void ali_seq_seed(AliSeqGrid &g1, const AliModel &m, const AliMatView &s
                           int cx1, int side1, double sign, int lane, int nlanes)
 {
     AliMat mat;
-    ali_fetch_mat(m, src_view, isz, isx, mat, true);
+    ali_fetch_mat(m, src_view, isz, isx, mat);
     const int w = 2 * side1 + 1;
     for (int q = lane; q < w * w; q += nlanes) {
         int i = q / w - side1, j = q % w - side1;
@@ -207,7 +207,7 @@ ALI_DEV void ali_seq_seed(AliSeqGrid &g1, const AliModel &m, const AliMatView &s
         if (!(0 <= cx1 + j && cx1 + j <= g1.nx - 1)) continue;
         double angle;
         if (j == 0) angle = 90.0;
-        else angle = ALI_RAD2DEG * atan((double)i / (double)j);
+        else angle = ALI_RAD2DEG * ALI_ATAN((double)i / (double)j);
         double eff = ali_pymod(mat.veln + sign * angle, 180.0);
         double vel;
         if (mat.velpn != 0) vel = ali_table_vel(m.group_tab, m.ncol, eff, mat.velpn, mat.vel_map);
@@ -333,9 +333,7 @@ ALI_DEV void ali_seq_source(const AliModel &m, const AliSourcePlan &p, const Ali
     cnt.pops = cnt.evals = cnt.fallbacks = 0;
     int overflow = 0;
     // view of the grid the levels refine: the coarse model (travel) or the sg-refined one
-    AliMatView base;
-    base.scale1 = 1; base.side1 = 0; base.z0 = 0; base.x0 = 0;
-    base.scale0 = p.fine ? p.sg : 1; base.side0 = p.fine ? (p.sg - 1) / 2 : 0; base.cast = p.fine ? 1 : 0;
+    const AliMatView base = ali_make_view(1, 0, 0, p.fine ? p.sg : 1, p.fine ? 1 : 0);
 
     for (int l = 0; l < p.nlev; l++) {
         const int cur = l & 1;
@@ -350,8 +348,7 @@ ALI_DEV void ali_seq_source(const AliModel &m, const AliSourcePlan &p, const Ali
         g.t_stride = g.nx;
         g.wz0 = 0; g.wx0 = 0; g.wnz = g.nz; g.wnx = g.nx;
         g.heap = sc.heap; g.heap_cap = sc.heap_cap;
-        g.mv = base;
-        g.mv.scale1 = scl; g.mv.side1 = (scl - 1) / 2; g.mv.z0 = bottom; g.mv.x0 = left; g.mv.cast = 1;
+        g.mv = ali_make_view(scl, bottom, left, p.fine ? p.sg : 1, 1);
         g.dnx = m.dnx / scl;
         cx[cur] = scl * (p.isx - left);
         cz[cur] = scl * (p.isz - bottom);

@@ -50,17 +50,20 @@ struct AliSourceRec {
     int src_iz, src_ix;     // coarse node
     AliSeqResult seq;       // window + counters of the sequential phase
     long long rounds, band_evals, band_fallbacks, max_band;
+    long long cycles[4];    // SM cycles spent in phases A0 / A1 / B / C (thread 0's view)
     int overflow;           // 1: sequential heap/window, 2: band list
 };
 
 struct AliBatch {
     AliModel m;
+    const AliModel *m_dev;  // the same struct in device memory (for out-of-line slow paths)
     int sg;
     int nz, nx;             // extents of the solved grid
     int margin;
     double delta;
     double *T;              // [n_src][nz*nx]
     uint8_t *st;            // [n_src][nz*nx]
+    uint8_t *dirty;         // [n_src][nz*nx]
     // sequential scratch, per source
     double *seq_t;          // [n_src][2*seq_cap]
     int32_t *seq_s;         // [n_src][2*seq_cap]
@@ -68,7 +71,7 @@ struct AliBatch {
     size_t seq_cap;
     int heap_cap;
     // band lists, per source
-    int *lists;             // [n_src][2*band_cap]
+    unsigned *lists;        // [n_src][2*band_cap] packed (iz << 16 | ix)
     double *stage;          // [n_src][band_cap]
     int band_cap;
     AliSourceRec *rec;      // [n_src]
@@ -77,6 +80,18 @@ struct AliBatch {
 // ---------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------
+// Builds the 64-byte per-node material records from the caller's arrays.
+__global__ void ali_records_kernel(int n, const double *veln, const int32_t *velpn, const double *vel_map,
+                                   const long long *stif, AliMatRec *rec)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        AliMatRec r;
+        r.veln = veln[i]; r.vel_map = vel_map[i]; r.velpn = velpn[i]; r.pad = 0;
+        for (int k = 0; k < 5; k++) r.s[k] = stif ? (double)stif[(size_t)5 * i + k] : 0.0;
+        rec[i] = r;
+    }
+}
+
 __global__ void ali_vmax_kernel(AliModel m, unsigned long long *out_bits)
 {
     const size_t n = (size_t)m.nz * m.nx;
@@ -130,34 +145,35 @@ __device__ __forceinline__ int ali_warp_reserve(int k, int *counter)
     return base + incl - k;
 }
 
-__global__ void __launch_bounds__(1024) ali_march_kernel(AliBatch b)
+template <int NT>
+__global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b)
 {
     const int src = blockIdx.x;
-    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int tid = threadIdx.x;
     AliSourceRec &rec = b.rec[src];
     __shared__ int s_count[2];
     __shared__ unsigned long long s_tmin[2];
     __shared__ int s_overflow;
     __shared__ unsigned long long s_evals, s_fbs;
+    __shared__ int s_work;
+    long long cyc[4] = {0, 0, 0, 0};
 
     AliBandGrid g;
     g.nz = b.nz; g.nx = b.nx;
     g.T = b.T + (size_t)src * b.nz * b.nx;
     g.st = b.st + (size_t)src * b.nz * b.nx;
+    g.dirty = b.dirty + (size_t)src * b.nz * b.nx;
     g.dnx = b.m.dnx;
-    g.mv.scale1 = 1; g.mv.side1 = 0; g.mv.z0 = 0; g.mv.x0 = 0;
-    g.mv.scale0 = b.sg > 1 ? b.sg : 1;
-    g.mv.side0 = b.sg > 1 ? (b.sg - 1) / 2 : 0;
-    g.mv.cast = b.sg > 1 ? 1 : 0;
-    int *list0 = b.lists + (size_t)src * 2 * b.band_cap;
-    int *list1 = list0 + b.band_cap;
+    g.mv = ali_band_view(b.sg);
+    unsigned *list0 = b.lists + (size_t)src * 2 * b.band_cap;
+    unsigned *list1 = list0 + b.band_cap;
     double *stage = b.stage + (size_t)src * b.band_cap;
 
     if (tid == 0) {
         s_count[0] = 0; s_count[1] = 0;
         s_tmin[0] = ~0ull; s_tmin[1] = ~0ull;
         s_overflow = rec.overflow;
-        s_evals = 0; s_fbs = 0;
+        s_evals = 0; s_fbs = 0; s_work = 0;
     }
     __syncthreads();
     if (s_overflow) return;
@@ -168,19 +184,23 @@ __global__ void __launch_bounds__(1024) ali_march_kernel(AliBatch b)
         const int nlev = b.sg > 1 ? 2 : 3;
         const int32_t *wst = b.seq_s + (size_t)src * 2 * b.seq_cap + ((((nlev - 1) & 1) == 0) ? b.seq_cap : 0);
         const int wn = w.wnz * w.wnx;
-        for (int base = 0; base < wn; base += nthr) {
+        for (int base = 0; base < wn; base += NT) {
             int i = base + tid;
-            int k = 0, node = 0;
+            int k = 0;
+            unsigned entry = 0;
             if (i < wn) {
                 int z = i / w.wnx, x = i - z * w.wnx;
                 int32_t s = wst[i];
-                node = (w.wz0 + z) * b.nx + (w.wx0 + x);
+                size_t node = (size_t)(w.wz0 + z) * b.nx + (w.wx0 + x);
                 if (s == 0) g.st[node] = ALI_ST_ALIVE;
-                else if (s > 0) { g.st[node] = ALI_ST_BAND; k = 1; }
+                else if (s > 0) {
+                    g.st[node] = ALI_ST_BAND; g.dirty[node] = 1; k = 1;
+                    entry = ALI_PACK(w.wz0 + z, w.wx0 + x);
+                }
             }
             int pos = ali_warp_reserve(k, &s_count[0]);
             if (k) {
-                if (pos < b.band_cap) list0[pos] = node;
+                if (pos < b.band_cap) list0[pos] = entry;
                 else s_overflow = 2;
             }
         }
@@ -193,43 +213,68 @@ __global__ void __launch_bounds__(1024) ali_march_kernel(AliBatch b)
     while (true) {
         const int n = s_count[cur];
         if (n == 0 || s_overflow) break;
-        int *list = cur == 0 ? list0 : list1;
-        int *next = cur == 0 ? list1 : list0;
+        unsigned *list = cur == 0 ? list0 : list1;
+        unsigned *next = cur == 0 ? list1 : list0;
         rounds++;
         if (n > max_band) max_band = n;
         if (tid == 0) s_tmin[cur ^ 1] = ~0ull;
-        // phase A: evaluate every band node from the round's snapshot
-        for (int i = tid; i < n; i += nthr) {
+        // phase A0: compact the band nodes whose window changed into a dense work list (the
+        // other list buffer is free until phase C); unchanged nodes keep their value
+        long long t0 = clock64();
+        for (int base = 0; base < n; base += NT) {
+            const int i = base + tid;
+            int k = 0;
+            if (i < n) {
+                const unsigned e = list[i];
+                const size_t node = (size_t)ALI_PACK_Z(e) * g.nx + ALI_PACK_X(e);
+                if (g.dirty[node]) { g.dirty[node] = 0; k = 1; }
+                else stage[i] = g.T[node];
+            }
+            int pos = ali_warp_reserve(k, &s_work);
+            if (k) next[pos] = (unsigned)i;
+        }
+        __syncthreads();
+        // phase A1: evaluate them from the round's snapshot
+        const int nwork = s_work;
+        long long t1 = clock64();
+        for (int q = tid; q < nwork; q += NT) {
+            const int i = (int)next[q];
+            const unsigned e = list[i];
+            const int iz = ALI_PACK_Z(e), ix = ALI_PACK_X(e);
             int fb = 0;
-            stage[i] = ali_band_eval(b.m, g, list[i], &fb);
+            stage[i] = ali_band_eval(b.m, b.m_dev, g, b.sg, iz, ix, &fb);
+            if (fb) g.dirty[(size_t)iz * g.nx + ix] = 1; // the fallback also reads alive flags: always re-evaluate
             my_evals++;
             my_fbs += fb;
         }
         __syncthreads();
+        long long t2 = clock64();
         // phase B: publish + tmin
-        if (tid == 0) s_count[cur] = 0;
+        if (tid == 0) { s_count[cur] = 0; s_work = 0; }
         double lmin = 1e300;
-        for (int i = tid; i < n; i += nthr) {
+        for (int i = tid; i < n; i += NT) {
+            const unsigned e = list[i];
             double v = stage[i];
-            ali_band_publish(g, list[i], v);
+            ali_band_publish(g, ALI_PACK_Z(e), ALI_PACK_X(e), v);
             lmin = fmin(lmin, v);
         }
         for (int o = 16; o > 0; o >>= 1) lmin = fmin(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
         if ((tid & 31) == 0 && lmin < 1e300)
             atomicMin(&s_tmin[cur], (unsigned long long)__double_as_longlong(lmin));
         __syncthreads();
+        long long t3 = clock64();
         // phase C: accept + extend the band, compacting into the other list
         const double thr = __longlong_as_double((long long)s_tmin[cur]) + b.delta;
-        for (int base = 0; base < n; base += nthr) {
+        for (int base = 0; base < n; base += NT) {
             int i = base + tid;
             int k = 0;
-            int out[4];
+            unsigned out[4];
             if (i < n) {
-                int node = list[i];
+                const unsigned e = list[i];
                 if (stage[i] <= thr) {
-                    k = ali_band_accept(g, node, out);
+                    k = ali_band_accept(g, ALI_PACK_Z(e), ALI_PACK_X(e), out);
                 } else {
-                    out[0] = node; k = 1;
+                    out[0] = e; k = 1;
                 }
             }
             int pos = ali_warp_reserve(k, &s_count[cur ^ 1]);
@@ -240,6 +285,10 @@ __global__ void __launch_bounds__(1024) ali_march_kernel(AliBatch b)
             }
         }
         __syncthreads();
+        if (tid == 0) {
+            long long t4 = clock64();
+            cyc[0] += t1 - t0; cyc[1] += t2 - t1; cyc[2] += t3 - t2; cyc[3] += t4 - t3;
+        }
         cur ^= 1;
     }
     atomicAdd(&s_evals, my_evals);
@@ -250,6 +299,7 @@ __global__ void __launch_bounds__(1024) ali_march_kernel(AliBatch b)
         rec.max_band = max_band;
         rec.band_evals = (long long)s_evals;
         rec.band_fallbacks = (long long)s_fbs;
+        for (int q = 0; q < 4; q++) rec.cycles[q] = cyc[q];
         if (s_overflow) rec.overflow = s_overflow;
     }
 }
@@ -400,7 +450,7 @@ __global__ void ali_minmax_kernel(AliModel m, int first_velpn, const double *col
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         int iz = (int)(i / m.nx), ix = (int)(i % m.nx);
         AliMat mat;
-        ali_fetch_mat(m, idv, iz, ix, mat, true);
+        ali_fetch_mat(m, idv, iz, ix, mat);
         if (first_velpn == 0) {
             for (int q = 0; q < 4; q++) {
                 double v = ali_christoffel_group(45.0 * q, mat.s, mat.vel_map);
@@ -434,6 +484,8 @@ struct alifmm_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     AliModel m{};           // device pointers
+    const AliModel *m_dev = nullptr;
+    int first_velpn = 0;
     int nz = 0, nx = 0;
     std::vector<void *> model_allocs;
     double vmax = 0.0;
@@ -444,7 +496,7 @@ struct alifmm_ctx {
     int threads_per_source = 1024;
     // resident batch
     int n_slots = 0, sg = 0, fz = 0, fx = 0;
-    DevBuf T, st, seq_t, seq_s, seq_heap, lists, stage, rec, jobs, ray_x, ray_y, ray_time, ray_len, ray_flag, misc;
+    DevBuf T, st, dirty, seq_t, seq_s, seq_heap, lists, stage, rec, jobs, ray_x, ray_y, ray_time, ray_len, ray_flag, misc;
     alifmm_counters_t cnt{};
 };
 
@@ -491,7 +543,7 @@ extern "C" void alifmm_destroy(alifmm_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (void *p : c->model_allocs) cudaFree(p);
-    DevBuf *bufs[] = {&c->T, &c->st, &c->seq_t, &c->seq_s, &c->seq_heap, &c->lists, &c->stage, &c->rec, &c->jobs,
+    DevBuf *bufs[] = {&c->T, &c->st, &c->dirty, &c->seq_t, &c->seq_s, &c->seq_heap, &c->lists, &c->stage, &c->rec, &c->jobs,
                       &c->ray_x, &c->ray_y, &c->ray_time, &c->ray_len, &c->ray_flag, &c->misc};
     for (DevBuf *b : bufs) dev_release(*b);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
@@ -526,22 +578,45 @@ extern "C" int alifmm_create(const alifmm_model_desc *d, int device, alifmm_ctx 
     c->nz = d->nz; c->nx = d->nx;
     c->m.nz = d->nz; c->m.nx = d->nx; c->m.dnx = d->dnx; c->m.ncol = d->n_cols;
     c->m.has_stif = d->has_stif ? 1 : 0;
-    if ((rc = upload(c, d->veln, n, &c->m.veln)) != 0) return bail(rc);
-    if ((rc = upload(c, d->velpn, n, &c->m.velpn)) != 0) return bail(rc);
-    if ((rc = upload(c, d->vel_map, n, &c->m.vel_map)) != 0) return bail(rc);
-    c->m.stif = nullptr;
-    if (d->stif_den) {
-        const long long *dp = nullptr;
-        if ((rc = upload(c, (const long long *)d->stif_den, n * 5, &dp)) != 0) return bail(rc);
-        c->m.stif = dp;
-    }
-    if ((rc = upload(c, d->group_vel, (size_t)361 * d->n_cols, &c->m.group_tab)) != 0) return bail(rc);
-    if ((rc = upload(c, d->phase_vel, (size_t)361 * d->n_cols, &c->m.phase_tab)) != 0) return bail(rc);
-    // material ids must index the tables
-    // (validated on the host: an out-of-range id would read outside the table on the device)
+    // material ids must index the tables (an out-of-range id would read outside them on the device)
     for (size_t i = 0; i < n; i++)
         if (d->velpn[i] < 0 || d->velpn[i] >= d->n_cols)
             return bail(fail(ALIFMM_E_INVALID, "alifmm_create: velpn holds a material id outside the velocity tables"));
+    c->first_velpn = d->velpn[0];
+    {   // raw arrays -> 64-byte records (the raw device copies are released afterwards)
+        const double *dv = nullptr, *dm = nullptr;
+        const int32_t *dp = nullptr;
+        const long long *ds = nullptr;
+        if ((rc = upload(c, d->veln, n, &dv)) != 0) return bail(rc);
+        if ((rc = upload(c, d->velpn, n, &dp)) != 0) return bail(rc);
+        if ((rc = upload(c, d->vel_map, n, &dm)) != 0) return bail(rc);
+        if (d->stif_den && (rc = upload(c, (const long long *)d->stif_den, n * 5, &ds)) != 0) return bail(rc);
+        void *recp = nullptr;
+        if (cudaMalloc(&recp, n * sizeof(AliMatRec)) != cudaSuccess)
+            return bail(fail(ALIFMM_E_CUDA, "alifmm_create: cudaMalloc(records) failed"));
+        int blocks = (int)((n + 255) / 256);
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        ali_records_kernel<<<blocks, 256, 0, c->stream>>>((int)n, dv, dp, dm, ds, (AliMatRec *)recp);
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess) {
+            cudaFree(recp);
+            return bail(fail(ALIFMM_E_CUDA, std::string("alifmm_create: records kernel failed: ") + cudaGetErrorString(cudaGetLastError())));
+        }
+        for (void *q : c->model_allocs) cudaFree(q);
+        c->model_allocs.clear();
+        c->model_allocs.push_back(recp);
+        c->m.rec = (const AliMatRec *)recp;
+    }
+    if ((rc = upload(c, d->group_vel, (size_t)361 * d->n_cols, &c->m.group_tab)) != 0) return bail(rc);
+    if ((rc = upload(c, d->phase_vel, (size_t)361 * d->n_cols, &c->m.phase_tab)) != 0) return bail(rc);
+    {   // the model struct itself, in device memory, for out-of-line slow paths
+        void *mp = nullptr;
+        if (cudaMalloc(&mp, sizeof(AliModel)) != cudaSuccess)
+            return bail(fail(ALIFMM_E_CUDA, "alifmm_create: cudaMalloc(model) failed"));
+        c->model_allocs.push_back(mp);
+        if (cudaMemcpyAsync(mp, &c->m, sizeof(AliModel), cudaMemcpyHostToDevice, c->stream) != cudaSuccess)
+            return bail(fail(ALIFMM_E_CUDA, "alifmm_create: model upload failed"));
+        c->m_dev = (const AliModel *)mp;
+    }
     // model-wide phase-velocity bound
     if ((rc = dev_reserve(c->misc, 64)) != 0) return bail(rc);
     if (cudaMemsetAsync(c->misc.p, 0, 64, c->stream) != cudaSuccess) return bail(fail(ALIFMM_E_CUDA, "memset failed"));
@@ -578,7 +653,7 @@ extern "C" int alifmm_set_option(alifmm_ctx *c, const char *name, double value)
         c->band_cap_factor = value;
     } else if (!strcmp(name, "threads_per_source")) {
         int t = (int)value;
-        if (t < 32 || t > 1024 || (t & 31)) return fail(ALIFMM_E_INVALID, "threads_per_source must be a multiple of 32 in [32, 1024]");
+        if (t != 256 && t != 512 && t != 1024) return fail(ALIFMM_E_INVALID, "threads_per_source must be 256, 512 or 1024");
         c->threads_per_source = t;
     } else {
         return fail(ALIFMM_E_INVALID, std::string("unknown option ") + name);
@@ -609,7 +684,8 @@ extern "C" int alifmm_ttf(alifmm_ctx *c, int32_t n_src, const int32_t *src_iz, c
     const size_t N = (size_t)fz * fx;
 
     AliBatch b;
-    b.m = c->m; b.sg = sg; b.nz = fz; b.nx = fx; b.margin = c->margin;
+    if (fz > 65535 || fx > 65535) return fail(ALIFMM_E_INVALID, "alifmm_ttf: grid side exceeds 65535 nodes");
+    b.m = c->m; b.m_dev = c->m_dev; b.sg = sg; b.nz = fz; b.nx = fx; b.margin = c->margin;
     b.delta = c->delta_frac * c->m.dnx / c->vmax;
     {   // scratch sizes from the plan (same for every source)
         AliSourcePlan p;
@@ -624,15 +700,16 @@ extern "C" int alifmm_ttf(alifmm_ctx *c, int32_t n_src, const int32_t *src_iz, c
     int rc;
     if ((rc = dev_reserve(c->T, (size_t)n_src * N * sizeof(double))) != 0) return rc;
     if ((rc = dev_reserve(c->st, (size_t)n_src * N + 16)) != 0) return rc;
+    if ((rc = dev_reserve(c->dirty, (size_t)n_src * N + 16)) != 0) return rc;
     if ((rc = dev_reserve(c->seq_t, (size_t)n_src * 2 * b.seq_cap * sizeof(double))) != 0) return rc;
     if ((rc = dev_reserve(c->seq_s, (size_t)n_src * 2 * b.seq_cap * sizeof(int32_t))) != 0) return rc;
     if ((rc = dev_reserve(c->seq_heap, (size_t)n_src * 2 * b.heap_cap * sizeof(int32_t))) != 0) return rc;
-    if ((rc = dev_reserve(c->lists, (size_t)n_src * 2 * b.band_cap * sizeof(int))) != 0) return rc;
+    if ((rc = dev_reserve(c->lists, (size_t)n_src * 2 * b.band_cap * sizeof(unsigned))) != 0) return rc;
     if ((rc = dev_reserve(c->stage, (size_t)n_src * b.band_cap * sizeof(double))) != 0) return rc;
     if ((rc = dev_reserve(c->rec, (size_t)n_src * sizeof(AliSourceRec))) != 0) return rc;
-    b.T = (double *)c->T.p; b.st = (uint8_t *)c->st.p;
+    b.T = (double *)c->T.p; b.st = (uint8_t *)c->st.p; b.dirty = (uint8_t *)c->dirty.p;
     b.seq_t = (double *)c->seq_t.p; b.seq_s = (int32_t *)c->seq_s.p; b.seq_heap = (int32_t *)c->seq_heap.p;
-    b.lists = (int *)c->lists.p; b.stage = (double *)c->stage.p; b.rec = (AliSourceRec *)c->rec.p;
+    b.lists = (unsigned *)c->lists.p; b.stage = (double *)c->stage.p; b.rec = (AliSourceRec *)c->rec.p;
 
     std::vector<AliSourceRec> recs(n_src);
     memset(recs.data(), 0, recs.size() * sizeof(AliSourceRec));
@@ -643,10 +720,13 @@ extern "C" int alifmm_ttf(alifmm_ctx *c, int32_t n_src, const int32_t *src_iz, c
     CUDA_TRY(cudaEventRecord(c->ev[0], s));
     CUDA_TRY(cudaMemsetAsync(b.T, 0, (size_t)n_src * N * sizeof(double), s));
     CUDA_TRY(cudaMemsetAsync(b.st, 0, (size_t)n_src * N, s));
+    CUDA_TRY(cudaMemsetAsync(b.dirty, 0, (size_t)n_src * N, s));
     ali_seq_kernel<<<n_src, 32, 0, s>>>(b);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(c->ev[1], s));
-    ali_march_kernel<<<n_src, c->threads_per_source, 0, s>>>(b);
+    if (c->threads_per_source >= 1024) ali_march_kernel<1024><<<n_src, 1024, 0, s>>>(b);
+    else if (c->threads_per_source >= 512) ali_march_kernel<512><<<n_src, 512, 0, s>>>(b);
+    else ali_march_kernel<256><<<n_src, 256, 0, s>>>(b);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(c->ev[2], s));
     int launches = 2;
@@ -683,6 +763,13 @@ extern "C" int alifmm_ttf(alifmm_ctx *c, int32_t n_src, const int32_t *src_iz, c
         cn.band_evals += r.band_evals;
         if (r.max_band > cn.max_band) cn.max_band = r.max_band;
         overflow |= r.overflow;
+    }
+    if (getenv("ALIFMM_DEBUG")) {
+        const AliSourceRec &r = recs[0];
+        fprintf(stderr, "[alifmm] source 0: rounds %lld, cycles/round A0 %.0f A1 %.0f B %.0f C %.0f, evals/round %.0f, band max %lld\n",
+                r.rounds, (double)r.cycles[0] / (r.rounds + 1e-9), (double)r.cycles[1] / (r.rounds + 1e-9),
+                (double)r.cycles[2] / (r.rounds + 1e-9), (double)r.cycles[3] / (r.rounds + 1e-9),
+                (double)r.band_evals / (r.rounds + 1e-9), r.max_band);
     }
     if (overflow & 2)
         return fail(ALIFMM_E_CAPACITY, "alifmm_ttf: narrow-band list overflowed; raise option band_capacity_factor");
@@ -823,8 +910,7 @@ extern "C" int alifmm_min_max_vel(alifmm_ctx *c, double *min_vel, double *max_ve
         }
         cmin[k] = lo; cmax[k] = hi;
     }
-    int first = 0;
-    CUDA_TRY(cudaMemcpy(&first, c->m.velpn, sizeof(int), cudaMemcpyDeviceToHost));
+    const int first = c->first_velpn;
     int rc;
     const size_t need = 64 + 2 * (size_t)c->m.ncol * sizeof(double);
     if ((rc = dev_reserve(c->misc, need > 2 * 361 * sizeof(double) + 64 ? need : 2 * 361 * sizeof(double) + 64)) != 0) return rc;

@@ -40,9 +40,19 @@ static double pymod(double a, double w)
     return m;
 }
 
+/* Diagnostic switch (default 0 = the reference's behaviour).  With 1 the narrow band is a
+ * correct min-heap: the parent of k is k/2 (the reference's round(k/2) picks a cousin for
+ * k = 3 mod 4, ATR:123) and a re-evaluated node is sifted down as well as up (the reference
+ * only sifts up, ATR:141-175, although its update may INCREASE a value).  Used by the tests
+ * to show that the CUDA path equals the reference algorithm with pops in true time order, and
+ * that it differs from the reference itself only downstream of heap mis-orderings. */
+static int g_true_heap = 0;
+void ali_oracle_set_true_heap(int on) { g_true_heap = on; }
+
 /* Python round(k / 2) for a positive int k: round-half-to-even (ATR:123,135,160,172). */
 static int half_round(int k)
 {
+    if (g_true_heap) return k >> 1;
     int h = k >> 1;
     if (k & 1) return (h & 1) ? h + 1 : h;
     return h;
@@ -77,6 +87,7 @@ typedef struct {
 #define AT(g, iz, ix) ((size_t)(iz) * (size_t)(g)->nx + (size_t)(ix))
 
 /* ---- heap (ATR:94-237) --------------------------------------------------- */
+static void sift_down_from(Grid *g, int tpp);
 static void addtree(Grid *g, int iz, int ix)
 {
     int tpc, tpp;
@@ -121,6 +132,29 @@ static void updtree(Grid *g, int iz, int ix)
         } else {
             tpp = 0;
         }
+    }
+    if (g_true_heap) sift_down_from(g, g->nsts[AT(g, iz, ix)]);
+}
+
+static void sift_down_from(Grid *g, int tpp)
+{
+    int ntr = g->ntr;
+    for (;;) {
+        int tpc = 2 * tpp, e0, e1;
+        double rc, rp;
+        if (tpc > ntr) break;
+        if (tpc + 1 <= ntr && g->ttn[AT(g, g->btg[2 * tpc], g->btg[2 * tpc + 1])] >
+                                  g->ttn[AT(g, g->btg[2 * tpc + 2], g->btg[2 * tpc + 3])])
+            tpc += 1;
+        rc = g->ttn[AT(g, g->btg[2 * tpc], g->btg[2 * tpc + 1])];
+        rp = g->ttn[AT(g, g->btg[2 * tpp], g->btg[2 * tpp + 1])];
+        if (!(rc < rp)) break;
+        g->nsts[AT(g, g->btg[2 * tpp], g->btg[2 * tpp + 1])] = tpc;
+        g->nsts[AT(g, g->btg[2 * tpc], g->btg[2 * tpc + 1])] = tpp;
+        e0 = g->btg[2 * tpc]; e1 = g->btg[2 * tpc + 1];
+        g->btg[2 * tpc] = g->btg[2 * tpp]; g->btg[2 * tpc + 1] = g->btg[2 * tpp + 1];
+        g->btg[2 * tpp] = e0; g->btg[2 * tpp + 1] = e1;
+        tpp = tpc;
     }
 }
 

@@ -144,6 +144,11 @@ def phase_vel(angle, c22, c23, c33, c44, sigma, vel_scale=1.0):
     return lib().ali_oracle_phase_vel(*[ctypes.c_double(float(v)) for v in (angle, c22, c23, c33, c44, sigma, vel_scale)])
 
 
+def set_true_heap(on):
+    """Diagnostic: make the narrow band a correct min-heap (see ali_oracle.c, g_true_heap)."""
+    lib().ali_oracle_set_true_heap(int(bool(on)))
+
+
 def counters(reset=False):
     u = ctypes.c_long(0)
     f = ctypes.c_long(0)

@@ -9,19 +9,46 @@
 #include <cstring>
 #include <cstdlib>
 #include <cstdio>
+#define ALI_EMU_NOISE 1
 #include "../../ali_fmm_and_ray_tracing_b200/csrc/ali_core.cuh"
 #include "../../ali_fmm_and_ray_tracing_b200/csrc/ali_seq.cuh"
 #include "../../ali_fmm_and_ray_tracing_b200/csrc/ali_band.cuh"
 #include "../../ali_fmm_and_ray_tracing_b200/csrc/ali_ray.cuh"
 
-static AliModel make_model(int nz, int nx, const double *veln, const int32_t *velpn, const double *vel_map,
-                           const long long *stif, int has_stif, const double *group_tab, const double *phase_tab,
-                           int ncol, double dnx)
+// Last-ulp noise on transcendental results (probability g_noise_p, +-1 ulp), to measure how
+// sensitive a solution is to the libm in use (GPU libm and glibc differ in the last ulps).
+static double g_noise_p = 0.0;
+static unsigned long long g_noise_state = 88172645463325252ull;
+double ali_emu_noise(double v)
 {
+    if (g_noise_p <= 0.0) return v;
+    g_noise_state ^= g_noise_state << 13; g_noise_state ^= g_noise_state >> 7; g_noise_state ^= g_noise_state << 17;
+    double u = (double)(g_noise_state >> 11) / 9007199254740992.0;
+    if (u >= g_noise_p) return v;
+    return nextafter(v, (g_noise_state & 1) ? 1e300 : -1e300);
+}
+extern "C" void emu_set_noise(double p, unsigned long long seed) { g_noise_p = p; if (seed) g_noise_state = seed; }
+
+struct HostModel {
+    std::vector<AliMatRec> rec;
     AliModel m;
-    m.nz = nz; m.nx = nx; m.veln = veln; m.velpn = velpn; m.vel_map = vel_map; m.stif = stif;
+};
+
+// Host replay of ali_records_kernel.
+static void make_model(HostModel &h, int nz, int nx, const double *veln, const int32_t *velpn,
+                       const double *vel_map, const long long *stif, int has_stif, const double *group_tab,
+                       const double *phase_tab, int ncol, double dnx)
+{
+    size_t n = (size_t)nz * nx;
+    h.rec.resize(n);
+    for (size_t i = 0; i < n; i++) {
+        AliMatRec &r = h.rec[i];
+        r.veln = veln[i]; r.vel_map = vel_map[i]; r.velpn = velpn[i]; r.pad = 0;
+        for (int k = 0; k < 5; k++) r.s[k] = stif ? (double)stif[5 * i + k] : 0.0;
+    }
+    AliModel &m = h.m;
+    m.nz = nz; m.nx = nx; m.rec = h.rec.data();
     m.has_stif = has_stif; m.group_tab = group_tab; m.phase_tab = phase_tab; m.ncol = ncol; m.dnx = dnx;
-    return m;
 }
 
 
@@ -62,7 +89,9 @@ extern "C" double emu_model_vmax(int nz, int nx, const double *veln, const int32
                                  const long long *stif, int has_stif, const double *group_tab,
                                  const double *phase_tab, int ncol, double dnx)
 {
-    AliModel m = make_model(nz, nx, veln, velpn, vel_map, stif, has_stif, group_tab, phase_tab, ncol, dnx);
+    HostModel hm;
+    make_model(hm, nz, nx, veln, velpn, vel_map, stif, has_stif, group_tab, phase_tab, ncol, dnx);
+    const AliModel &m = hm.m;
     double best = 0.0;
     for (int iz = 0; iz < nz; iz++)
         for (int ix = 0; ix < nx; ix++) {
@@ -76,10 +105,12 @@ extern "C" double emu_model_vmax(int nz, int nx, const double *veln, const int32
 //           [5] band fallbacks, [6] max list length, [7] overflow flag
 extern "C" int emu_ttf(int nz, int nx, const double *veln, const int32_t *velpn, const double *vel_map,
                        const long long *stif, int has_stif, const double *group_tab, const double *phase_tab,
-                       int ncol, double dnx, int src_iz, int src_ix, int sg, int margin, double delta, double *T,
-                       long long *counters)
+                       int ncol, double dnx, int src_iz, int src_ix, int sg, int margin, double delta, int eager,
+                       double *T, long long *counters)
 {
-    AliModel m = make_model(nz, nx, veln, velpn, vel_map, stif, has_stif, group_tab, phase_tab, ncol, dnx);
+    HostModel hm;
+    make_model(hm, nz, nx, veln, velpn, vel_map, stif, has_stif, group_tab, phase_tab, ncol, dnx);
+    const AliModel &m = hm.m;
     AliSourcePlan p;
     ali_make_plan(p, m, src_iz, src_ix, sg, margin);
     const size_t n = (size_t)p.nz * p.nx;
@@ -99,20 +130,19 @@ extern "C" int emu_ttf(int nz, int nx, const double *veln, const int32_t *velpn,
     if (res.overflow) return -1;
 
     // ---- band-synchronous march (replay of ali_march_kernel) ----
-    std::vector<uint8_t> status(n, ALI_ST_FAR);
-    std::vector<int> list, next;
+    std::vector<uint8_t> status(n, ALI_ST_FAR), dirty(n, 0);
+    std::vector<unsigned> list, next;
     const int32_t *wst = ((p.nlev - 1) & 1) == 0 ? sc.sB : sc.sA;
     for (int z = 0; z < res.wnz; z++)
         for (int x = 0; x < res.wnx; x++) {
             int32_t s = wst[(size_t)z * res.wnx + x];
             size_t node = (size_t)(res.wz0 + z) * p.nx + (res.wx0 + x);
             if (s == 0) status[node] = ALI_ST_ALIVE;
-            else if (s > 0) { status[node] = ALI_ST_BAND; list.push_back((int)node); }
+            else if (s > 0) { status[node] = ALI_ST_BAND; dirty[node] = 1; list.push_back(ALI_PACK(res.wz0 + z, res.wx0 + x)); }
         }
     AliBandGrid bg;
-    bg.nz = p.nz; bg.nx = p.nx; bg.T = T; bg.st = status.data(); bg.dnx = m.dnx;
-    bg.mv.scale1 = 1; bg.mv.side1 = 0; bg.mv.z0 = 0; bg.mv.x0 = 0;
-    bg.mv.scale0 = p.fine ? p.sg : 1; bg.mv.side0 = p.fine ? (p.sg - 1) / 2 : 0; bg.mv.cast = p.fine ? 1 : 0;
+    bg.nz = p.nz; bg.nx = p.nx; bg.T = T; bg.st = status.data(); bg.dirty = dirty.data(); bg.dnx = m.dnx;
+    bg.mv = ali_band_view(sg);
     std::vector<double> tnew;
     long long rounds = 0, evals = 0, fbs = 0, maxlist = 0;
     while (!list.empty()) {
@@ -120,25 +150,32 @@ extern "C" int emu_ttf(int nz, int nx, const double *veln, const int32_t *velpn,
         if ((long long)list.size() > maxlist) maxlist = (long long)list.size();
         tnew.resize(list.size());
         for (size_t i = 0; i < list.size(); i++) {
-            int fb = 0;
-            tnew[i] = ali_band_eval(m, bg, list[i], &fb);
-            evals++; fbs += fb;
+            const int iz = ALI_PACK_Z(list[i]), ix = ALI_PACK_X(list[i]);
+            const size_t node = (size_t)iz * p.nx + ix;
+            if (dirty[node] || eager) {
+                int fb = 0;
+                dirty[node] = 0;
+                tnew[i] = ali_band_eval(m, &m, bg, sg, iz, ix, &fb);
+                if (fb) dirty[node] = 1;
+                evals++; fbs += fb;
+            } else {
+                tnew[i] = T[node];
+            }
         }
         double tmin = 1e300;
         for (size_t i = 0; i < list.size(); i++) {
-            ali_band_publish(bg, list[i], tnew[i]);
+            ali_band_publish(bg, ALI_PACK_Z(list[i]), ALI_PACK_X(list[i]), tnew[i]);
             if (tnew[i] < tmin) tmin = tnew[i];
         }
         const double thr = tmin + delta;
         next.clear();
         for (size_t i = 0; i < list.size(); i++) {
-            int node = list[i];
             if (tnew[i] <= thr) {
-                int nb[4];
-                int cnt = ali_band_accept(bg, node, nb);
+                unsigned nb[4];
+                int cnt = ali_band_accept(bg, ALI_PACK_Z(list[i]), ALI_PACK_X(list[i]), nb);
                 for (int k = 0; k < cnt; k++) next.push_back(nb[k]);
             } else {
-                next.push_back(node);
+                next.push_back(list[i]);
             }
         }
         list.swap(next);
@@ -155,6 +192,8 @@ extern "C" int emu_find_ray(int nz, int nx, const double *veln, const int32_t *v
                             double ry, double *ray_x, double *ray_y, int cap, double *time_out, int *flag_out,
                             int nlanes)
 {
-    AliModel m = make_model(nz, nx, veln, velpn, vel_map, stif, has_stif, group_tab, group_tab, ncol, dnx);
+    HostModel hm;
+    make_model(hm, nz, nx, veln, velpn, vel_map, stif, has_stif, group_tab, group_tab, ncol, dnx);
+    const AliModel &m = hm.m;
     return ali_emu_trace_ray(m, sg, rec_ttf, fz, fx, sx, sy, rx, ry, ray_x, ray_y, cap, time_out, flag_out, nlanes);
 }

@@ -31,11 +31,16 @@ def _margs(m, dnx):
             int(m.has_stif), _p(m.group, _f64p), _p(m.phase, _f64p), m.ncol, ctypes.c_double(dnx))
 
 
+def set_noise(p, seed=0):
+    """Last-ulp noise on sin/cos/tan/atan results with probability p (sensitivity studies)."""
+    lib().emu_set_noise(ctypes.c_double(p), ctypes.c_ulonglong(seed))
+
+
 def model_vmax(m, dnx):
     return lib().emu_model_vmax(*_margs(m, dnx))
 
 
-def ttf(m, dnx, src_iz, src_ix, sg=1, margin=27, frac=0.25, vmax=None):
+def ttf(m, dnx, src_iz, src_ix, sg=1, margin=27, frac=0.25, vmax=None, eager=False):
     """Replays seq-init + band march for one source; m is an oracle.ali_oracle.Model."""
     if vmax is None:
         vmax = model_vmax(m, dnx)
@@ -45,7 +50,7 @@ def ttf(m, dnx, src_iz, src_ix, sg=1, margin=27, frac=0.25, vmax=None):
     T = np.zeros((nz, nx))
     cnt = np.zeros(8, dtype=np.int64)
     rc = lib().emu_ttf(*_margs(m, dnx), int(src_iz), int(src_ix), int(sg), int(margin), ctypes.c_double(delta),
-                       _p(T, _f64p), cnt.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)))
+                       int(eager), _p(T, _f64p), cnt.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)))
     names = ["seq_pops", "seq_evals", "seq_fallbacks", "rounds", "band_evals", "band_fallbacks", "max_list", "overflow"]
     return T, dict(zip(names, cnt.tolist())), rc
 

@@ -1,0 +1,134 @@
+"""CPU: the host-side mirror of the reference interface, the C ABI surface and the sharding."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from tests import models
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(built_library):
+    """Every function include/alifmm.h declares is exported by libalifmm.so (no compute call)."""
+    hdr = open(os.path.join(ROOT, "include", "alifmm.h")).read()
+    declared = set(re.findall(r"\b(alifmm_[a-z_]+)\s*\(", hdr))
+    declared.discard("alifmm_ctx")
+    assert len(declared) >= 14
+    lib = ctypes.CDLL(built_library)
+    for name in sorted(declared):
+        assert hasattr(lib, name), name
+    from ali_fmm_and_ray_tracing_b200 import _capi
+    assert set(_capi.EXPORTS) == declared
+
+
+def test_no_gpu_means_loud_failure(built_library):
+    """There is no CPU fallback: without a device the compute entry points raise."""
+    from ali_fmm_and_ray_tracing_b200 import _capi
+    if _capi.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    g = np.ones((361, 2))
+    with pytest.raises(_capi.AlifmmError) as ei:
+        _capi.Context(np.zeros((8, 8)), np.ones((8, 8), dtype=int), np.ones((8, 8)), None, True, g, g, 1e-3)
+    assert "no CUDA device" in str(ei.value)
+    from Anis_TTF_rays import ALI_FMM
+    m = models.notebook_gradient(21)
+    fm = ALI_FMM(m["veln"], m["velpn"], m["vel_map"], m["scx"][:1] * 0.1, m["scz"][:1] * 0.1)
+    with pytest.raises(_capi.AlifmmError):
+        fm.update(m["veln"], m["velpn"], m["vel_map"])
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "ali_fmm_and_ray_tracing_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "ali_oracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
+
+
+def test_constructor_mirrors_reference_errors():
+    from Anis_TTF_rays import ALI_FMM
+    m = models.notebook_gradient(11)
+    with pytest.raises(TypeError):  # velpn must be integer (ATR:3834-3838)
+        ALI_FMM(m["veln"], m["velpn"].astype(float), m["vel_map"], m["scx"], m["scz"])
+    with pytest.raises(TypeError):  # stif_den must be int64 (ATR:3821-3822)
+        ALI_FMM(m["veln"], m["velpn"], m["vel_map"], m["scx"], m["scz"], stif_den=np.zeros((11, 11, 5), dtype=np.int32))
+    fm = ALI_FMM(m["veln"], m["velpn"], m["vel_map"], np.array([0.0012, 0.0095]), np.array([0.003, 0.0085]))
+    assert fm.velocity_dat.shape == (361, 2) and np.all(fm.velocity_dat[:, 0] == np.arange(361))
+    assert list(fm.isx) == [1.0, 10.0] and list(fm.isz) == [3.0, 8.0]  # banker's round as the reference
+    assert fm.nnx == 11 and fm.nnz == 11 and fm.nsrc == 2 and fm.dnz == fm.dnx == 1e-3
+    assert fm.ray_paths_x is None and fm.ray_len is None
+    with pytest.raises(ValueError):  # ATR:4573-4574
+        fm.find_all_TTF_rays_parallel(m["veln"], m["velpn"], m["vel_map"], n_threads=1)
+
+
+def test_material_tables_match_reference():
+    """generate_group_vel / generate_phase_vel / add_materials (ATR:4112-4256) vs the fixture
+    produced by the reference's own class."""
+    from Anis_TTF_rays import ALI_FMM
+    z = np.load(os.path.join(ROOT, "tests", "golden", "golden_fields.npz"))
+    g = ALI_FMM.generate_group_vel(None, *models.STEEL_PA, False)
+    p = ALI_FMM.generate_phase_vel(None, *models.STEEL_PA, False)
+    assert np.array_equal(g, z["nb2_group"][:, 1]) and np.array_equal(p, z["nb2_phase"][:, 1])
+    m = models.notebook_gradient(11)
+    fm = ALI_FMM(m["veln"], m["velpn"], m["vel_map"], m["scx"], m["scz"])
+    fm.add_materials(np.array(models.STEEL_PA))
+    assert fm.velocity_dat.shape == (361, 2) and np.array_equal(fm.velocity_dat[:, 1], g)
+    fm.add_materials(np.array(models.STEEL_PA), keep_materials=True)
+    assert fm.velocity_dat.shape == (361, 3) and np.array_equal(fm.phase_vel[:, 2], p)
+    two = np.array([models.STEEL_PA, models.STEEL_PA], dtype=float)
+    fm.add_materials(two, keep_materials=True)  # the reference sizes by materials.shape[1] (ATR:4228)
+    assert fm.velocity_dat.shape == (361, 3 + 5)
+
+
+def test_shard_bounds_cover_and_balance():
+    from ali_fmm_and_ray_tracing_b200.sharding import shard_bounds
+    for n in (0, 1, 7, 128, 129):
+        for w in (1, 2, 3, 8):
+            parts = [shard_bounds(n, w, r) for r in range(w)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(w - 1))
+            sizes = [b - a for a, b in parts]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    import torch
+    from ali_fmm_and_ray_tracing_b200.sharding import shard_indices
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    mine = shard_indices(13, world, rank)
+    # each rank "solves" its sources (here: records which ones) -- no collective on the data path;
+    # only the bench-style reduction of counters / times crosses ranks
+    owner = torch.full((13,), -1, dtype=torch.int64)
+    owner[mine] = rank
+    gathered = [torch.empty_like(owner) for _ in range(world)]
+    dist.all_gather(gathered, owner)
+    t = torch.tensor([float(len(mine))])
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    tmax = torch.tensor([1.0 + rank])
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        merged = torch.stack(gathered).max(dim=0).values
+        q.put((merged.tolist(), t.item(), tmax.item()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_world_size_2_sharding_over_gloo():
+    """N > 1 path on CPU: sources are partitioned, nothing is exchanged but counters / times."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    merged, total, tmax = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert merged == [0] * 7 + [1] * 6 and total == 13.0 and tmax == 2.0
