@@ -138,7 +138,6 @@ ALI_DEV bool ali_band_claim(const AliBandGrid &g, size_t node)
 #else
     g.st[node] = ALI_ST_QUEUED;
 #endif
-    g.dirty[node] = 1;
     return true;
 }
 

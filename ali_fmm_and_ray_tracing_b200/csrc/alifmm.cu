@@ -145,17 +145,52 @@ __device__ __forceinline__ int ali_warp_reserve(int k, int *counter)
     return base + incl - k;
 }
 
-template <int NT>
-__global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b)
+// Two warp-aggregated appends at once (next-list slot and work-list slot).
+__device__ __forceinline__ void ali_warp_reserve2(int k, int kw, int *counter, int *wcounter, int &pos, int &wpos)
 {
+    const unsigned lane = threadIdx.x & 31;
+    int incl = k | (kw << 16); // k <= 4, kw <= 4: both prefix sums in one scan
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (unsigned)o) incl += v;
+    }
+    int total = __shfl_sync(0xffffffffu, incl, 31);
+    int base = 0, wbase = 0;
+    if (lane == 31) {
+        if (total & 0xffff) base = atomicAdd(counter, total & 0xffff);
+        if (total >> 16) wbase = atomicAdd(wcounter, total >> 16);
+    }
+    base = __shfl_sync(0xffffffffu, base, 31);
+    wbase = __shfl_sync(0xffffffffu, wbase, 31);
+    pos = base + (incl & 0xffff) - k;
+    wpos = wbase + (incl >> 16) - kw;
+}
+
+// Band-synchronous march of one source per CTA (ali_band.cuh).  The narrow band lives in
+// shared memory when it fits (packed entries and the round's work list, 16 bytes per band
+// node; their values stay in global memory so that L1 keeps room for the T / status
+// gathers), else in the global buffers of the batch.
+//   round r:  A  evaluate the work list (band nodes whose window changed) -> value[i]
+//             -- barrier --
+//             B  publish those values (T, status, dirty marks); tmin = min(all band values)
+//             -- barrier --
+//             C  accept value <= tmin + delta (alive, enlist far neighbours), compact the
+//                survivors into the other buffer, build the next work list and the minimum
+//                of the values that will not be re-evaluated
+//             -- barrier --
+template <int NT>
+__global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
+{
+    extern __shared__ __align__(16) unsigned char s_raw[];
     const int src = blockIdx.x;
     const int tid = threadIdx.x;
     AliSourceRec &rec = b.rec[src];
     __shared__ int s_count[2];
-    __shared__ unsigned long long s_tmin[2];
+    __shared__ int s_nwork[2];
+    __shared__ unsigned long long s_evalmin[2], s_basemin[2];
     __shared__ int s_overflow;
     __shared__ unsigned long long s_evals, s_fbs;
-    __shared__ int s_work;
     long long cyc[4] = {0, 0, 0, 0};
 
     AliBandGrid g;
@@ -165,20 +200,30 @@ __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b)
     g.dirty = b.dirty + (size_t)src * b.nz * b.nx;
     g.dnx = b.m.dnx;
     g.mv = ali_band_view(b.sg);
-    unsigned *list0 = b.lists + (size_t)src * 2 * b.band_cap;
-    unsigned *list1 = list0 + b.band_cap;
-    double *stage = b.stage + (size_t)src * b.band_cap;
+
+    // band storage: value[2][cap] f64 (global), entry[2][cap] u32, work[2][cap] (index into entry)
+    const int cap = b.band_cap;
+    double *val0 = b.stage + (size_t)src * 2 * cap, *val1 = val0 + cap;
+    unsigned *ent0, *ent1, *wrk0, *wrk1;
+    if (smem_cap >= cap) {
+        ent0 = (unsigned *)s_raw; ent1 = ent0 + cap;
+        wrk0 = ent1 + cap; wrk1 = wrk0 + cap;
+    } else {
+        ent0 = b.lists + (size_t)src * 4 * cap; ent1 = ent0 + cap;
+        wrk0 = ent1 + cap; wrk1 = wrk0 + cap;
+    }
 
     if (tid == 0) {
-        s_count[0] = 0; s_count[1] = 0;
-        s_tmin[0] = ~0ull; s_tmin[1] = ~0ull;
+        s_count[0] = 0; s_count[1] = 0; s_nwork[0] = 0; s_nwork[1] = 0;
+        s_evalmin[0] = ~0ull; s_evalmin[1] = ~0ull; s_basemin[0] = ~0ull; s_basemin[1] = ~0ull;
         s_overflow = rec.overflow;
-        s_evals = 0; s_fbs = 0; s_work = 0;
+        s_evals = 0; s_fbs = 0;
     }
     __syncthreads();
     if (s_overflow) return;
 
-    // hand-over: window statuses of the sequential phase -> byte statuses + first band list
+    // hand-over: window statuses of the sequential phase -> byte statuses + first band list;
+    // every band node starts dirty (in the work list)
     {
         const AliSeqResult w = rec.seq;
         const int nlev = b.sg > 1 ? 2 : 3;
@@ -193,18 +238,17 @@ __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b)
                 int32_t s = wst[i];
                 size_t node = (size_t)(w.wz0 + z) * b.nx + (w.wx0 + x);
                 if (s == 0) g.st[node] = ALI_ST_ALIVE;
-                else if (s > 0) {
-                    g.st[node] = ALI_ST_BAND; g.dirty[node] = 1; k = 1;
-                    entry = ALI_PACK(w.wz0 + z, w.wx0 + x);
-                }
+                else if (s > 0) { g.st[node] = ALI_ST_BAND; k = 1; entry = ALI_PACK(w.wz0 + z, w.wx0 + x); }
             }
             int pos = ali_warp_reserve(k, &s_count[0]);
             if (k) {
-                if (pos < b.band_cap) list0[pos] = entry;
+                if (pos < cap) { ent0[pos] = entry; wrk0[pos] = (unsigned)pos; }
                 else s_overflow = 2;
             }
         }
     }
+    __syncthreads();
+    if (tid == 0) s_nwork[0] = s_count[0];
     __syncthreads();
 
     long long rounds = 0, max_band = 0;
@@ -213,81 +257,87 @@ __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b)
     while (true) {
         const int n = s_count[cur];
         if (n == 0 || s_overflow) break;
-        unsigned *list = cur == 0 ? list0 : list1;
-        unsigned *next = cur == 0 ? list1 : list0;
+        const int nwork = s_nwork[cur];
+        double *val = cur == 0 ? val0 : val1, *nval = cur == 0 ? val1 : val0;
+        unsigned *ent = cur == 0 ? ent0 : ent1, *nent = cur == 0 ? ent1 : ent0;
+        unsigned *wrk = cur == 0 ? wrk0 : wrk1, *nwrk = cur == 0 ? wrk1 : wrk0;
         rounds++;
         if (n > max_band) max_band = n;
-        if (tid == 0) s_tmin[cur ^ 1] = ~0ull;
-        // phase A0: compact the band nodes whose window changed into a dense work list (the
-        // other list buffer is free until phase C); unchanged nodes keep their value
         long long t0 = clock64();
-        for (int base = 0; base < n; base += NT) {
-            const int i = base + tid;
-            int k = 0;
-            if (i < n) {
-                const unsigned e = list[i];
-                const size_t node = (size_t)ALI_PACK_Z(e) * g.nx + ALI_PACK_X(e);
-                if (g.dirty[node]) { g.dirty[node] = 0; k = 1; }
-                else stage[i] = g.T[node];
-            }
-            int pos = ali_warp_reserve(k, &s_work);
-            if (k) next[pos] = (unsigned)i;
-        }
-        __syncthreads();
-        // phase A1: evaluate them from the round's snapshot
-        const int nwork = s_work;
-        long long t1 = clock64();
+        // phase A: evaluate the work list from the round's snapshot
         for (int q = tid; q < nwork; q += NT) {
-            const int i = (int)next[q];
-            const unsigned e = list[i];
+            const int i = (int)wrk[q];
+            const unsigned e = ent[i];
             const int iz = ALI_PACK_Z(e), ix = ALI_PACK_X(e);
             int fb = 0;
-            stage[i] = ali_band_eval(b.m, b.m_dev, g, b.sg, iz, ix, &fb);
+            g.dirty[(size_t)iz * g.nx + ix] = 0;
+            val[i] = ali_band_eval(b.m, b.m_dev, g, b.sg, iz, ix, &fb);
             if (fb) g.dirty[(size_t)iz * g.nx + ix] = 1; // the fallback also reads alive flags: always re-evaluate
             my_evals++;
             my_fbs += fb;
         }
         __syncthreads();
-        long long t2 = clock64();
-        // phase B: publish + tmin
-        if (tid == 0) { s_count[cur] = 0; s_work = 0; }
+        long long t1 = clock64();
+        // phase B: publish the re-evaluated values; tmin over the whole band
+        if (tid == 0) { s_count[cur ^ 1] = 0; s_nwork[cur ^ 1] = 0; s_basemin[cur ^ 1] = ~0ull; s_evalmin[cur ^ 1] = ~0ull; }
         double lmin = 1e300;
-        for (int i = tid; i < n; i += NT) {
-            const unsigned e = list[i];
-            double v = stage[i];
+        for (int q = tid; q < nwork; q += NT) {
+            const int i = (int)wrk[q];
+            const unsigned e = ent[i];
+            const double v = val[i];
             ali_band_publish(g, ALI_PACK_Z(e), ALI_PACK_X(e), v);
             lmin = fmin(lmin, v);
         }
         for (int o = 16; o > 0; o >>= 1) lmin = fmin(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
         if ((tid & 31) == 0 && lmin < 1e300)
-            atomicMin(&s_tmin[cur], (unsigned long long)__double_as_longlong(lmin));
+            atomicMin(&s_evalmin[cur], (unsigned long long)__double_as_longlong(lmin));
         __syncthreads();
-        long long t3 = clock64();
-        // phase C: accept + extend the band, compacting into the other list
-        const double thr = __longlong_as_double((long long)s_tmin[cur]) + b.delta;
+        long long t2 = clock64();
+        // phase C: accept + extend the band; compact survivors; next work list
+        const unsigned long long tminb = s_evalmin[cur] < s_basemin[cur] ? s_evalmin[cur] : s_basemin[cur];
+        const double thr = __longlong_as_double((long long)tminb) + b.delta;
+        double bmin = 1e300;
         for (int base = 0; base < n; base += NT) {
-            int i = base + tid;
-            int k = 0;
+            const int i = base + tid;
+            int k = 0, kw = 0;
             unsigned out[4];
+            double v = 0.0;
             if (i < n) {
-                const unsigned e = list[i];
-                if (stage[i] <= thr) {
-                    k = ali_band_accept(g, ALI_PACK_Z(e), ALI_PACK_X(e), out);
+                const unsigned e = ent[i];
+                v = val[i];
+                const int iz = ALI_PACK_Z(e), ix = ALI_PACK_X(e);
+                if (v <= thr) {
+                    k = ali_band_accept(g, iz, ix, out); // new nodes: always evaluated next round
+                    kw = k;
+                    v = 0.0;
                 } else {
                     out[0] = e; k = 1;
+                    const size_t node = (size_t)iz * g.nx + ix;
+                    if (g.dirty[node]) { g.dirty[node] = 0; kw = 1; }
+                    else bmin = fmin(bmin, v);
                 }
             }
-            int pos = ali_warp_reserve(k, &s_count[cur ^ 1]);
-            if (pos + k <= b.band_cap) {
-                for (int q = 0; q < k; q++) next[pos + q] = out[q];
+            int pos, wpos;
+            ali_warp_reserve2(k, kw, &s_count[cur ^ 1], &s_nwork[cur ^ 1], pos, wpos);
+            if (pos + k <= cap) {
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (q < k) {
+                        nent[pos + q] = out[q];
+                        nval[pos + q] = v;
+                        if (q < kw) nwrk[wpos + q] = (unsigned)(pos + q);
+                    }
             } else if (k) {
                 s_overflow = 2;
             }
         }
+        for (int o = 16; o > 0; o >>= 1) bmin = fmin(bmin, __shfl_xor_sync(0xffffffffu, bmin, o));
+        if ((tid & 31) == 0 && bmin < 1e300)
+            atomicMin(&s_basemin[cur ^ 1], (unsigned long long)__double_as_longlong(bmin));
         __syncthreads();
         if (tid == 0) {
-            long long t4 = clock64();
-            cyc[0] += t1 - t0; cyc[1] += t2 - t1; cyc[2] += t3 - t2; cyc[3] += t4 - t3;
+            long long t3 = clock64();
+            cyc[0] += t1 - t0; cyc[1] += t2 - t1; cyc[2] += t3 - t2;
         }
         cur ^= 1;
     }
@@ -494,6 +544,7 @@ struct alifmm_ctx {
     int margin = 27;
     double band_cap_factor = 6.0;
     int threads_per_source = 1024;
+    int band_smem_bytes = 0;   // measured on B200: L1 for the T / status gathers is worth more than smem lists
     // resident batch
     int n_slots = 0, sg = 0, fz = 0, fx = 0;
     DevBuf T, st, dirty, seq_t, seq_s, seq_heap, lists, stage, rec, jobs, ray_x, ray_y, ray_time, ray_len, ray_flag, misc;
@@ -655,6 +706,9 @@ extern "C" int alifmm_set_option(alifmm_ctx *c, const char *name, double value)
         int t = (int)value;
         if (t != 256 && t != 512 && t != 1024) return fail(ALIFMM_E_INVALID, "threads_per_source must be 256, 512 or 1024");
         c->threads_per_source = t;
+    } else if (!strcmp(name, "band_smem_kb")) {
+        if (value < 0 || value > 200) return fail(ALIFMM_E_INVALID, "band_smem_kb must be in [0, 200]");
+        c->band_smem_bytes = (int)value * 1024;
     } else {
         return fail(ALIFMM_E_INVALID, std::string("unknown option ") + name);
     }
@@ -668,8 +722,24 @@ extern "C" int alifmm_set_stream(alifmm_ctx *c, void *s)
     return ALIFMM_OK;
 }
 
+static int ttf_attempt(alifmm_ctx *c, int32_t n_src, const int32_t *src_iz, const int32_t *src_ix, int32_t sg,
+                       double *out_host, int band_cap_override, int *band_overflow);
+
 extern "C" int alifmm_ttf(alifmm_ctx *c, int32_t n_src, const int32_t *src_iz, const int32_t *src_ix, int32_t sg,
                           double *out_host)
+{
+    // first try a narrow-band capacity that fits in shared memory; a band that outgrows it
+    // (closed fronts of interior sources on large grids) is re-run from global buffers
+    int overflow = 0;
+    if (c && c->band_smem_bytes >= 16 * 2048) {
+        int rc = ttf_attempt(c, n_src, src_iz, src_ix, sg, out_host, c->band_smem_bytes / 16, &overflow);
+        if (rc != ALIFMM_E_CAPACITY || !overflow) return rc;
+    }
+    return ttf_attempt(c, n_src, src_iz, src_ix, sg, out_host, 0, &overflow);
+}
+
+static int ttf_attempt(alifmm_ctx *c, int32_t n_src, const int32_t *src_iz, const int32_t *src_ix, int32_t sg,
+                       double *out_host, int band_cap_override, int *band_overflow)
 {
     if (!c || !src_iz || !src_ix) return fail(ALIFMM_E_INVALID, "alifmm_ttf: null argument");
     if (n_src < 1) return fail(ALIFMM_E_INVALID, "alifmm_ttf: n_src must be >= 1");
@@ -697,6 +767,8 @@ extern "C" int alifmm_ttf(alifmm_ctx *c, int32_t n_src, const int32_t *src_iz, c
         b.heap_cap = (int)(cap / 2 + 64);
     }
     b.band_cap = (int)(c->band_cap_factor * (double)(fz + fx)) + 1024;
+    if (band_cap_override > 0 && band_cap_override < b.band_cap) b.band_cap = band_cap_override;
+    *band_overflow = 0;
     int rc;
     if ((rc = dev_reserve(c->T, (size_t)n_src * N * sizeof(double))) != 0) return rc;
     if ((rc = dev_reserve(c->st, (size_t)n_src * N + 16)) != 0) return rc;
@@ -704,8 +776,8 @@ extern "C" int alifmm_ttf(alifmm_ctx *c, int32_t n_src, const int32_t *src_iz, c
     if ((rc = dev_reserve(c->seq_t, (size_t)n_src * 2 * b.seq_cap * sizeof(double))) != 0) return rc;
     if ((rc = dev_reserve(c->seq_s, (size_t)n_src * 2 * b.seq_cap * sizeof(int32_t))) != 0) return rc;
     if ((rc = dev_reserve(c->seq_heap, (size_t)n_src * 2 * b.heap_cap * sizeof(int32_t))) != 0) return rc;
-    if ((rc = dev_reserve(c->lists, (size_t)n_src * 2 * b.band_cap * sizeof(unsigned))) != 0) return rc;
-    if ((rc = dev_reserve(c->stage, (size_t)n_src * b.band_cap * sizeof(double))) != 0) return rc;
+    if ((rc = dev_reserve(c->lists, (size_t)n_src * 4 * b.band_cap * sizeof(unsigned))) != 0) return rc;
+    if ((rc = dev_reserve(c->stage, (size_t)n_src * 2 * b.band_cap * sizeof(double))) != 0) return rc;
     if ((rc = dev_reserve(c->rec, (size_t)n_src * sizeof(AliSourceRec))) != 0) return rc;
     b.T = (double *)c->T.p; b.st = (uint8_t *)c->st.p; b.dirty = (uint8_t *)c->dirty.p;
     b.seq_t = (double *)c->seq_t.p; b.seq_s = (int32_t *)c->seq_s.p; b.seq_heap = (int32_t *)c->seq_heap.p;
@@ -724,9 +796,22 @@ extern "C" int alifmm_ttf(alifmm_ctx *c, int32_t n_src, const int32_t *src_iz, c
     ali_seq_kernel<<<n_src, 32, 0, s>>>(b);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(c->ev[1], s));
-    if (c->threads_per_source >= 1024) ali_march_kernel<1024><<<n_src, 1024, 0, s>>>(b);
-    else if (c->threads_per_source >= 512) ali_march_kernel<512><<<n_src, 512, 0, s>>>(b);
-    else ali_march_kernel<256><<<n_src, 256, 0, s>>>(b);
+    {
+        // band entries + work lists in shared memory when they fit in c->band_smem_bytes
+        size_t need = (size_t)b.band_cap * 16;
+        int smem_cap = need <= (size_t)c->band_smem_bytes ? b.band_cap : 0;
+        size_t smem = smem_cap ? need : 0;
+        if (c->threads_per_source >= 1024) {
+            CUDA_TRY(cudaFuncSetAttribute(ali_march_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ali_march_kernel<1024><<<n_src, 1024, smem, s>>>(b, smem_cap);
+        } else if (c->threads_per_source >= 512) {
+            CUDA_TRY(cudaFuncSetAttribute(ali_march_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ali_march_kernel<512><<<n_src, 512, smem, s>>>(b, smem_cap);
+        } else {
+            CUDA_TRY(cudaFuncSetAttribute(ali_march_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ali_march_kernel<256><<<n_src, 256, smem, s>>>(b, smem_cap);
+        }
+    }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(c->ev[2], s));
     int launches = 2;
@@ -766,11 +851,12 @@ extern "C" int alifmm_ttf(alifmm_ctx *c, int32_t n_src, const int32_t *src_iz, c
     }
     if (getenv("ALIFMM_DEBUG")) {
         const AliSourceRec &r = recs[0];
-        fprintf(stderr, "[alifmm] source 0: rounds %lld, cycles/round A0 %.0f A1 %.0f B %.0f C %.0f, evals/round %.0f, band max %lld\n",
+        fprintf(stderr, "[alifmm] source 0: rounds %lld, cycles/round A %.0f B %.0f C %.0f, evals/round %.0f, band max %lld\n",
                 r.rounds, (double)r.cycles[0] / (r.rounds + 1e-9), (double)r.cycles[1] / (r.rounds + 1e-9),
-                (double)r.cycles[2] / (r.rounds + 1e-9), (double)r.cycles[3] / (r.rounds + 1e-9),
+                (double)r.cycles[2] / (r.rounds + 1e-9),
                 (double)r.band_evals / (r.rounds + 1e-9), r.max_band);
     }
+    if (overflow & 2) *band_overflow = 1;
     if (overflow & 2)
         return fail(ALIFMM_E_CAPACITY, "alifmm_ttf: narrow-band list overflowed; raise option band_capacity_factor");
     if (overflow & 1)

@@ -83,7 +83,8 @@ void alifmm_destroy(alifmm_ctx *ctx);
  * be <= 0.4), "handover_margin" (nodes the sequential replica runs past the last
  * refined source box, default 27), "band_capacity_factor" (narrow-band list capacity as
  * a multiple of nz+nx of the solved grid, default 6), "threads_per_source" (CTA size of
- * the band march, default 1024). */
+ * the band march: 256, 512 or 1024, default 1024), "band_smem_kb" (shared memory for the
+ * band lists, default 0 = keep L1 for the field gathers). */
 int alifmm_set_option(alifmm_ctx *ctx, const char *name, double value);
 
 /* Runs the library's kernels on the caller's CUDA stream (a cudaStream_t passed as

@@ -173,7 +173,10 @@ extern "C" int emu_ttf(int nz, int nx, const double *veln, const int32_t *velpn,
             if (tnew[i] <= thr) {
                 unsigned nb[4];
                 int cnt = ali_band_accept(bg, ALI_PACK_Z(list[i]), ALI_PACK_X(list[i]), nb);
-                for (int k = 0; k < cnt; k++) next.push_back(nb[k]);
+                for (int k = 0; k < cnt; k++) {
+                    next.push_back(nb[k]);   // new nodes are always evaluated next round (kernel: work list)
+                    dirty[(size_t)ALI_PACK_Z(nb[k]) * p.nx + ALI_PACK_X(nb[k])] = 1;
+                }
             } else {
                 next.push_back(list[i]);
             }
