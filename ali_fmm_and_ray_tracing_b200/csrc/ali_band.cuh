@@ -17,11 +17,14 @@
 #pragma once
 #include "ali_core.cuh"
 
-// Node status of the band march.  avail (reference: nsts >= 0) <=> status >= BAND.
+// Node state of the band march.  Availability to stencils (reference: nsts >= 0) is carried
+// by the travel time itself: a node without an estimate holds NaN (the field is pre-filled
+// with 0xFF bytes), so the 12-neighbour gather reads one array instead of two.  The status
+// byte only distinguishes far / enlisted / alive (phase C and the FD fallback).
 #define ALI_ST_FAR 0
 #define ALI_ST_QUEUED 1
-#define ALI_ST_BAND 2
 #define ALI_ST_ALIVE 3
+#define ALI_T_UNSET_BYTE 0xFF
 
 // Band list entries pack the node as (iz << 16) | ix (grids up to 65535 x 65535).
 #define ALI_PACK(iz, ix) (((unsigned)(iz) << 16) | (unsigned)(ix))
@@ -35,7 +38,7 @@ struct AliBandGrid {
     uint8_t *dirty;   // [nz*nx] 1: window changed since the node's last evaluation
     AliMatView mv;
     double dnx;
-    ALI_DEV bool avail(int z, int x) const { return st[(size_t)z * nx + x] >= ALI_ST_BAND; }
+    ALI_DEV bool avail(int z, int x) const { return T[(size_t)z * nx + x] >= 0.0; } // false for NaN
     ALI_DEV bool alive(int z, int x) const { return st[(size_t)z * nx + x] == ALI_ST_ALIVE; }
     ALI_DEV double tt(int z, int x) const { return T[(size_t)z * nx + x]; }
 };
@@ -49,17 +52,14 @@ ALI_HD AliMatView ali_band_view(int sg)
 ALI_DEV void ali_band_gather(const AliBandGrid &g, int iz, int ix, AliWindow &w)
 {
     if (iz >= 2 && iz < g.nz - 2 && ix >= 2 && ix < g.nx - 2) {
-        const size_t c = (size_t)iz * g.nx + ix;
-        const uint8_t *sp = g.st + c;
-        const double *tp = g.T + c;
+        const double *tp = g.T + ((size_t)iz * g.nx + ix);
         const int nx = g.nx;
         unsigned av = 0;
 #pragma unroll
-        for (int k = 0; k < 12; k++) {
-            const int off = ALI_W_DZ(k) * nx + ALI_W_DX(k);
-            w.t[k] = tp[off];
-            if (sp[off] >= ALI_ST_BAND) av |= 1u << k;
-        }
+        for (int k = 0; k < 12; k++) w.t[k] = tp[ALI_W_DZ(k) * nx + ALI_W_DX(k)];
+#pragma unroll
+        for (int k = 0; k < 12; k++)
+            if (w.t[k] >= 0.0) av |= 1u << k;
         w.avail = av;
     } else {
         ali_gather(g, iz, ix, g.nz, g.nx, w);
@@ -116,10 +116,8 @@ ALI_DEV void ali_band_mark_dirty(const AliBandGrid &g, int iz, int ix)
 ALI_DEV void ali_band_publish(const AliBandGrid &g, int iz, int ix, double v)
 {
     const size_t node = (size_t)iz * g.nx + ix;
-    const bool fresh = g.st[node] == ALI_ST_QUEUED;
-    if (fresh || g.T[node] != v) {
+    if (!(g.T[node] == v)) {   // also true for a node without an estimate yet (NaN)
         g.T[node] = v;
-        if (fresh) g.st[node] = ALI_ST_BAND;
         ali_band_mark_dirty(g, iz, ix);
     }
 }

@@ -49,12 +49,12 @@ double ali_emu_noise(double v);
 // the caller's arrays (veln f64, velpn i32, vel_map f64, stif_den i64[5]): the int64
 // stiffness entries are converted to fp64 once (exact below 2^53) instead of per evaluation.
 // ---------------------------------------------------------------------------
-struct AliMatRec {
+struct AliMatRec {   // two 32-byte sectors: tabulated materials only touch the first
     double veln;     // orientation, degrees (as passed by the caller)
     double vel_map;  // velocity scale (as passed by the caller)
-    double s[5];     // c22, c23, c33, c44 [MPa], rho; zeros when the model has no stif_den
     int velpn;       // material id (0 = Christoffel from s[])
     int pad;
+    double s[5];     // c22, c23, c33, c44 [MPa], rho; zeros when the model has no stif_den
 };
 
 struct AliModel {
@@ -117,7 +117,13 @@ ALI_DEV void ali_fetch_mat(const AliModel &m, const AliMatView &v, int iz, int i
     int cz = ali_div_by(pz + v.side0, v.scale0, v.mul0);
     int cx = ali_div_by(px + v.side0, v.scale0, v.mul0);
     const AliMatRec *r = m.rec + ((size_t)cz * (size_t)m.nx + (size_t)cx);
+#if defined(__CUDA_ARCH__)
+    // one 16-byte load for (veln, vel_map) instead of two 8-byte ones
+    const double2 vv = __ldg(reinterpret_cast<const double2 *>(r));
+    double vn = vv.x, vm = vv.y;
+#else
     double vn = r->veln, vm = r->vel_map;
+#endif
     if (v.cast) {
         vn = (double)(int)vn;
         vm = (double)(float)vm;

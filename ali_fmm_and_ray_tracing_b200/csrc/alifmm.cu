@@ -238,7 +238,8 @@ __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
                 int32_t s = wst[i];
                 size_t node = (size_t)(w.wz0 + z) * b.nx + (w.wx0 + x);
                 if (s == 0) g.st[node] = ALI_ST_ALIVE;
-                else if (s > 0) { g.st[node] = ALI_ST_BAND; k = 1; entry = ALI_PACK(w.wz0 + z, w.wx0 + x); }
+                else if (s > 0) { g.st[node] = ALI_ST_QUEUED; k = 1; entry = ALI_PACK(w.wz0 + z, w.wx0 + x); }
+                else g.T[node] = __longlong_as_double(-1ll); // far: the hand-off copied 0 here (ATR:2010); no estimate = NaN
             }
             int pos = ali_warp_reserve(k, &s_count[0]);
             if (k) {
@@ -354,10 +355,13 @@ __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
     }
 }
 
+// T / subgrid (ATR:2832); nodes the march never reached keep the reference's 0.
 __global__ void ali_finalize_kernel(double *T, size_t n, int sg)
 {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-        T[i] = T[i] / sg;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        double v = T[i];
+        T[i] = (v >= 0.0) ? v / sg : 0.0;
+    }
 }
 
 struct AliRayJob {
@@ -790,7 +794,7 @@ static int ttf_attempt(alifmm_ctx *c, int32_t n_src, const int32_t *src_iz, cons
     cudaStream_t s = c->stream;
     CUDA_TRY(cudaMemcpyAsync(b.rec, recs.data(), recs.size() * sizeof(AliSourceRec), cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaEventRecord(c->ev[0], s));
-    CUDA_TRY(cudaMemsetAsync(b.T, 0, (size_t)n_src * N * sizeof(double), s));
+    CUDA_TRY(cudaMemsetAsync(b.T, ALI_T_UNSET_BYTE, (size_t)n_src * N * sizeof(double), s)); // NaN = no estimate
     CUDA_TRY(cudaMemsetAsync(b.st, 0, (size_t)n_src * N, s));
     CUDA_TRY(cudaMemsetAsync(b.dirty, 0, (size_t)n_src * N, s));
     ali_seq_kernel<<<n_src, 32, 0, s>>>(b);
@@ -814,14 +818,13 @@ static int ttf_attempt(alifmm_ctx *c, int32_t n_src, const int32_t *src_iz, cons
     }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(c->ev[2], s));
-    int launches = 2;
-    if (sg > 1) {
+    int launches = 3;
+    {
         size_t total = (size_t)n_src * N;
         int blocks = (int)((total + 255) / 256);
         if (blocks > 148 * 16) blocks = 148 * 16;
         ali_finalize_kernel<<<blocks, 256, 0, s>>>(b.T, total, sg);
         CUDA_TRY(cudaGetLastError());
-        launches++;
     }
     CUDA_TRY(cudaEventRecord(c->ev[3], s));
     CUDA_TRY(cudaMemcpyAsync(recs.data(), b.rec, recs.size() * sizeof(AliSourceRec), cudaMemcpyDeviceToHost, s));

@@ -122,7 +122,7 @@ extern "C" int emu_ttf(int nz, int nx, const double *veln, const int32_t *velpn,
     AliSeqScratch sc;
     sc.tA = tA.data(); sc.tB = tB.data(); sc.sA = sA.data(); sc.sB = sB.data();
     sc.heap = heap.data(); sc.heap_cap = (int)(cap / 2 + 64); sc.status_cap = cap;
-    std::memset(T, 0, n * sizeof(double));
+    std::memset(T, ALI_T_UNSET_BYTE, n * sizeof(double)); // NaN = no estimate
     AliSeqResult res;
     ali_seq_source(m, p, sc, T, res, 0, 1);
     counters[0] = res.cnt.pops; counters[1] = res.cnt.evals; counters[2] = res.cnt.fallbacks;
@@ -138,7 +138,8 @@ extern "C" int emu_ttf(int nz, int nx, const double *veln, const int32_t *velpn,
             int32_t s = wst[(size_t)z * res.wnx + x];
             size_t node = (size_t)(res.wz0 + z) * p.nx + (res.wx0 + x);
             if (s == 0) status[node] = ALI_ST_ALIVE;
-            else if (s > 0) { status[node] = ALI_ST_BAND; dirty[node] = 1; list.push_back(ALI_PACK(res.wz0 + z, res.wx0 + x)); }
+            else if (s > 0) { status[node] = ALI_ST_QUEUED; dirty[node] = 1; list.push_back(ALI_PACK(res.wz0 + z, res.wx0 + x)); }
+            else { long long bits = -1; std::memcpy(&T[node], &bits, 8); }
         }
     AliBandGrid bg;
     bg.nz = p.nz; bg.nx = p.nx; bg.T = T; bg.st = status.data(); bg.dirty = dirty.data(); bg.dnx = m.dnx;
@@ -183,8 +184,7 @@ extern "C" int emu_ttf(int nz, int nx, const double *veln, const int32_t *velpn,
         }
         list.swap(next);
     }
-    if (p.fine)
-        for (size_t i = 0; i < n; i++) T[i] = T[i] / p.sg; // ATR:2832
+    for (size_t i = 0; i < n; i++) T[i] = (T[i] >= 0.0) ? T[i] / p.sg : 0.0; // ATR:2832
     counters[3] = rounds; counters[4] = evals; counters[5] = fbs; counters[6] = maxlist;
     return 0;
 }

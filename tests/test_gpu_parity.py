@@ -117,9 +117,9 @@ def test_weld_coarse_fields_match_reference_golden(capi, orc):
     T = ctx.ttf(src[:, 1].astype(np.int32), src[:, 0].astype(np.int32), 1)
     for k in range(len(src)):
         _check_field(gold["weld1_sub"][k], T[k][::4, ::4], worst=1e-4, med=1e-7, what=k)
-        assert abs(T[k].sum() - gold["weld1_sum"][k]) <= 1e-9 * gold["weld1_sum"][k]
+        assert abs(T[k].sum() - gold["weld1_sum"][k]) <= 1e-7 * gold["weld1_sum"][k]
     c = ctx.counters()
-    assert c["node_solves"] == 4 * 424 * 500 and c["band_rounds_max"] > 100 and c["kernel_launches"] == 2
+    assert c["node_solves"] == 4 * 424 * 500 and c["band_rounds_max"] > 100 and c["kernel_launches"] == 3
     ctx.close()
 
 
