@@ -17,14 +17,19 @@
 #pragma once
 #include "ali_core.cuh"
 
-// Node state of the band march.  Availability to stencils (reference: nsts >= 0) is carried
-// by the travel time itself: a node without an estimate holds NaN (the field is pre-filled
-// with 0xFF bytes), so the 12-neighbour gather reads one array instead of two.  The status
-// byte only distinguishes far / enlisted / alive (phase C and the FD fallback).
+// Node state of the band march lives in the travel-time word itself:
+//   far       NaN, all bits set (the field is pre-filled with 0xFF bytes)
+//   enlisted  NaN, lowest bit clear: in the band list, no estimate published yet
+//   estimate  any value >= 0: available to stencils (reference: nsts >= 0), tentative or final
+// so the 12-neighbour gather and the enlisting of far neighbours touch one array (whose
+// sectors the gathers keep in L1).  A separate byte per node records "alive"; it is written
+// once per node and read only by the FD fallback.  Dirty flags are bytes in 16 x 8-node tiles
+// (one 128-byte line each) so that vertical band segments do not take one line per node.
 #define ALI_ST_FAR 0
-#define ALI_ST_QUEUED 1
 #define ALI_ST_ALIVE 3
 #define ALI_T_UNSET_BYTE 0xFF
+#define ALI_T_FAR_BITS 0xFFFFFFFFFFFFFFFFull
+#define ALI_T_ENLISTED_BITS 0xFFFFFFFFFFFFFFFEull
 
 // Band list entries pack the node as (iz << 16) | ix (grids up to 65535 x 65535).
 #define ALI_PACK(iz, ix) (((unsigned)(iz) << 16) | (unsigned)(ix))
@@ -34,14 +39,22 @@
 struct AliBandGrid {
     int nz, nx;
     double *T;        // [nz*nx] travel times of this source (seconds * sg on the fine path)
-    uint8_t *st;      // [nz*nx] status
-    uint8_t *dirty;   // [nz*nx] 1: window changed since the node's last evaluation
+    uint8_t *st;      // [nz*nx] ALI_ST_ALIVE once accepted
+    uint8_t *dirty;   // tiled [tiles_z][tiles_x][8][16]; 1: window changed since the node's last evaluation
+    int tiles_x;
     AliMatView mv;
     double dnx;
     ALI_DEV bool avail(int z, int x) const { return T[(size_t)z * nx + x] >= 0.0; } // false for NaN
     ALI_DEV bool alive(int z, int x) const { return st[(size_t)z * nx + x] == ALI_ST_ALIVE; }
     ALI_DEV double tt(int z, int x) const { return T[(size_t)z * nx + x]; }
 };
+
+ALI_HD int ali_dirty_tiles_x(int nx) { return (nx + 15) >> 4; }
+ALI_HD size_t ali_dirty_bytes(int nz, int nx) { return (size_t)((nz + 7) >> 3) * (size_t)ali_dirty_tiles_x(nx) * 128; }
+ALI_DEV size_t ali_dirty_index(const AliBandGrid &g, int iz, int ix)
+{
+    return ((size_t)(iz >> 3) * g.tiles_x + (size_t)(ix >> 4)) * 128 + (size_t)(((iz & 7) << 4) | (ix & 15));
+}
 
 ALI_HD AliMatView ali_band_view(int sg)
 {
@@ -73,7 +86,7 @@ ALI_DEV_NOINLINE double ali_band_fouds_slow(const AliModel *m_dev, double *T, ui
 {
     AliModel m = *m_dev;
     AliBandGrid g;
-    g.nz = nz; g.nx = nx; g.T = T; g.st = st; g.dirty = nullptr; g.mv = ali_band_view(sg); g.dnx = dnx;
+    g.nz = nz; g.nx = nx; g.T = T; g.st = st; g.dirty = nullptr; g.tiles_x = 0; g.mv = ali_band_view(sg); g.dnx = dnx;
     AliMat mat;
     ali_fetch_mat(m, g.mv, iz, ix, mat);
     return ali_fouds18(m, mat, g, iz, ix, dnx, dnx, nx, nz);
@@ -99,15 +112,21 @@ ALI_DEV double ali_band_eval(const AliModel &m, const AliModel *m_dev, const Ali
 ALI_DEV void ali_band_mark_dirty(const AliBandGrid &g, int iz, int ix)
 {
     if (iz >= 2 && iz < g.nz - 2 && ix >= 2 && ix < g.nx - 2) {
-        uint8_t *dp = g.dirty + (size_t)iz * g.nx + ix;
-        const int nx = g.nx;
+        // tiled address = row term + column term
+        size_t rt[5], ct[5];
 #pragma unroll
-        for (int k = 0; k < 12; k++) dp[ALI_W_DZ(k) * nx + ALI_W_DX(k)] = 1;
+        for (int q = 0; q < 5; q++) {
+            const int z = iz + q - 2, x = ix + q - 2;
+            rt[q] = (size_t)(z >> 3) * g.tiles_x * 128 + (size_t)((z & 7) << 4);
+            ct[q] = (size_t)(x >> 4) * 128 + (size_t)(x & 15);
+        }
+#pragma unroll
+        for (int k = 0; k < 12; k++) g.dirty[rt[ALI_W_DZ(k) + 2] + ct[ALI_W_DX(k) + 2]] = 1;
     } else {
 #pragma unroll
         for (int k = 0; k < 12; k++) {
             int z = iz + ALI_W_DZ(k), x = ix + ALI_W_DX(k);
-            if (z >= 0 && z < g.nz && x >= 0 && x < g.nx) g.dirty[(size_t)z * g.nx + x] = 1;
+            if (z >= 0 && z < g.nz && x >= 0 && x < g.nx) g.dirty[ali_dirty_index(g, z, x)] = 1;
         }
     }
 }
@@ -125,18 +144,15 @@ ALI_DEV void ali_band_publish(const AliBandGrid &g, int iz, int ix, double v)
 // Claims a far node for the band list; returns true for exactly one caller.
 ALI_DEV bool ali_band_claim(const AliBandGrid &g, size_t node)
 {
-    if (g.st[node] != ALI_ST_FAR) return false;
+    unsigned long long *w = (unsigned long long *)(g.T + node);
 #if defined(__CUDA_ARCH__)
-    // byte-wide claim through a 32-bit atomicOr on the containing word: within phase C a
-    // FAR byte can only turn QUEUED, so OR-ing bit 0 never corrupts another state.
-    unsigned *word = (unsigned *)((uintptr_t)(g.st + node) & ~(uintptr_t)3);
-    unsigned shift = 8u * (unsigned)((uintptr_t)(g.st + node) & 3);
-    unsigned old = atomicOr(word, (unsigned)ALI_ST_QUEUED << shift);
-    if (((old >> shift) & 0xffu) != ALI_ST_FAR) return false;
+    if (*(volatile unsigned long long *)w != ALI_T_FAR_BITS) return false;
+    return atomicCAS(w, ALI_T_FAR_BITS, ALI_T_ENLISTED_BITS) == ALI_T_FAR_BITS;
 #else
-    g.st[node] = ALI_ST_QUEUED;
-#endif
+    if (*w != ALI_T_FAR_BITS) return false;
+    *w = ALI_T_ENLISTED_BITS;
     return true;
+#endif
 }
 
 // Phase C for an accepted node: alive + enlist far 4-neighbours (the reference's visiting

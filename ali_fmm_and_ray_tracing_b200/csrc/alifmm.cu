@@ -197,7 +197,8 @@ __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
     g.nz = b.nz; g.nx = b.nx;
     g.T = b.T + (size_t)src * b.nz * b.nx;
     g.st = b.st + (size_t)src * b.nz * b.nx;
-    g.dirty = b.dirty + (size_t)src * b.nz * b.nx;
+    g.dirty = b.dirty + (size_t)src * ali_dirty_bytes(b.nz, b.nx);
+    g.tiles_x = ali_dirty_tiles_x(b.nx);
     g.dnx = b.m.dnx;
     g.mv = ali_band_view(b.sg);
 
@@ -238,8 +239,8 @@ __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
                 int32_t s = wst[i];
                 size_t node = (size_t)(w.wz0 + z) * b.nx + (w.wx0 + x);
                 if (s == 0) g.st[node] = ALI_ST_ALIVE;
-                else if (s > 0) { g.st[node] = ALI_ST_QUEUED; k = 1; entry = ALI_PACK(w.wz0 + z, w.wx0 + x); }
-                else g.T[node] = __longlong_as_double(-1ll); // far: the hand-off copied 0 here (ATR:2010); no estimate = NaN
+                else if (s > 0) { k = 1; entry = ALI_PACK(w.wz0 + z, w.wx0 + x); } // holds an estimate: not claimable
+                else g.T[node] = __longlong_as_double((long long)ALI_T_FAR_BITS); // far: the hand-off copied 0 here (ATR:2010)
             }
             int pos = ali_warp_reserve(k, &s_count[0]);
             if (k) {
@@ -271,9 +272,10 @@ __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
             const unsigned e = ent[i];
             const int iz = ALI_PACK_Z(e), ix = ALI_PACK_X(e);
             int fb = 0;
-            g.dirty[(size_t)iz * g.nx + ix] = 0;
+            const size_t di = ali_dirty_index(g, iz, ix);
+            g.dirty[di] = 0;
             val[i] = ali_band_eval(b.m, b.m_dev, g, b.sg, iz, ix, &fb);
-            if (fb) g.dirty[(size_t)iz * g.nx + ix] = 1; // the fallback also reads alive flags: always re-evaluate
+            if (fb) g.dirty[di] = 1; // the fallback also reads alive flags: always re-evaluate
             my_evals++;
             my_fbs += fb;
         }
@@ -313,8 +315,8 @@ __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
                     v = 0.0;
                 } else {
                     out[0] = e; k = 1;
-                    const size_t node = (size_t)iz * g.nx + ix;
-                    if (g.dirty[node]) { g.dirty[node] = 0; kw = 1; }
+                    const size_t di = ali_dirty_index(g, iz, ix);
+                    if (g.dirty[di]) { g.dirty[di] = 0; kw = 1; }
                     else bmin = fmin(bmin, v);
                 }
             }
@@ -776,7 +778,8 @@ static int ttf_attempt(alifmm_ctx *c, int32_t n_src, const int32_t *src_iz, cons
     int rc;
     if ((rc = dev_reserve(c->T, (size_t)n_src * N * sizeof(double))) != 0) return rc;
     if ((rc = dev_reserve(c->st, (size_t)n_src * N + 16)) != 0) return rc;
-    if ((rc = dev_reserve(c->dirty, (size_t)n_src * N + 16)) != 0) return rc;
+    const size_t dirty_bytes = ali_dirty_bytes(fz, fx);
+    if ((rc = dev_reserve(c->dirty, (size_t)n_src * dirty_bytes + 16)) != 0) return rc;
     if ((rc = dev_reserve(c->seq_t, (size_t)n_src * 2 * b.seq_cap * sizeof(double))) != 0) return rc;
     if ((rc = dev_reserve(c->seq_s, (size_t)n_src * 2 * b.seq_cap * sizeof(int32_t))) != 0) return rc;
     if ((rc = dev_reserve(c->seq_heap, (size_t)n_src * 2 * b.heap_cap * sizeof(int32_t))) != 0) return rc;
@@ -796,7 +799,7 @@ static int ttf_attempt(alifmm_ctx *c, int32_t n_src, const int32_t *src_iz, cons
     CUDA_TRY(cudaEventRecord(c->ev[0], s));
     CUDA_TRY(cudaMemsetAsync(b.T, ALI_T_UNSET_BYTE, (size_t)n_src * N * sizeof(double), s)); // NaN = no estimate
     CUDA_TRY(cudaMemsetAsync(b.st, 0, (size_t)n_src * N, s));
-    CUDA_TRY(cudaMemsetAsync(b.dirty, 0, (size_t)n_src * N, s));
+    CUDA_TRY(cudaMemsetAsync(b.dirty, 0, (size_t)n_src * dirty_bytes, s));
     ali_seq_kernel<<<n_src, 32, 0, s>>>(b);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(c->ev[1], s));

@@ -130,7 +130,7 @@ extern "C" int emu_ttf(int nz, int nx, const double *veln, const int32_t *velpn,
     if (res.overflow) return -1;
 
     // ---- band-synchronous march (replay of ali_march_kernel) ----
-    std::vector<uint8_t> status(n, ALI_ST_FAR), dirty(n, 0);
+    std::vector<uint8_t> status(n, ALI_ST_FAR), dirty(ali_dirty_bytes(p.nz, p.nx), 0);
     std::vector<unsigned> list, next;
     const int32_t *wst = ((p.nlev - 1) & 1) == 0 ? sc.sB : sc.sA;
     for (int z = 0; z < res.wnz; z++)
@@ -138,11 +138,13 @@ extern "C" int emu_ttf(int nz, int nx, const double *veln, const int32_t *velpn,
             int32_t s = wst[(size_t)z * res.wnx + x];
             size_t node = (size_t)(res.wz0 + z) * p.nx + (res.wx0 + x);
             if (s == 0) status[node] = ALI_ST_ALIVE;
-            else if (s > 0) { status[node] = ALI_ST_QUEUED; dirty[node] = 1; list.push_back(ALI_PACK(res.wz0 + z, res.wx0 + x)); }
-            else { long long bits = -1; std::memcpy(&T[node], &bits, 8); }
+            else if (s > 0) { list.push_back(ALI_PACK(res.wz0 + z, res.wx0 + x)); }
+            else { unsigned long long bits = ALI_T_FAR_BITS; std::memcpy(&T[node], &bits, 8); }
         }
     AliBandGrid bg;
     bg.nz = p.nz; bg.nx = p.nx; bg.T = T; bg.st = status.data(); bg.dirty = dirty.data(); bg.dnx = m.dnx;
+    bg.tiles_x = ali_dirty_tiles_x(p.nx);
+    for (size_t i = 0; i < list.size(); i++) dirty[ali_dirty_index(bg, ALI_PACK_Z(list[i]), ALI_PACK_X(list[i]))] = 1;
     bg.mv = ali_band_view(sg);
     std::vector<double> tnew;
     long long rounds = 0, evals = 0, fbs = 0, maxlist = 0;
@@ -153,11 +155,12 @@ extern "C" int emu_ttf(int nz, int nx, const double *veln, const int32_t *velpn,
         for (size_t i = 0; i < list.size(); i++) {
             const int iz = ALI_PACK_Z(list[i]), ix = ALI_PACK_X(list[i]);
             const size_t node = (size_t)iz * p.nx + ix;
-            if (dirty[node] || eager) {
+            const size_t di = ali_dirty_index(bg, iz, ix);
+            if (dirty[di] || eager) {
                 int fb = 0;
-                dirty[node] = 0;
+                dirty[di] = 0;
                 tnew[i] = ali_band_eval(m, &m, bg, sg, iz, ix, &fb);
-                if (fb) dirty[node] = 1;
+                if (fb) dirty[di] = 1;
                 evals++; fbs += fb;
             } else {
                 tnew[i] = T[node];
@@ -176,7 +179,7 @@ extern "C" int emu_ttf(int nz, int nx, const double *veln, const int32_t *velpn,
                 int cnt = ali_band_accept(bg, ALI_PACK_Z(list[i]), ALI_PACK_X(list[i]), nb);
                 for (int k = 0; k < cnt; k++) {
                     next.push_back(nb[k]);   // new nodes are always evaluated next round (kernel: work list)
-                    dirty[(size_t)ALI_PACK_Z(nb[k]) * p.nx + ALI_PACK_X(nb[k])] = 1;
+                    dirty[ali_dirty_index(bg, ALI_PACK_Z(nb[k]), ALI_PACK_X(nb[k]))] = 1;
                 }
             } else {
                 next.push_back(list[i]);
