@@ -74,6 +74,7 @@ struct AliBatch {
     unsigned *lists;        // [n_src][2*band_cap] packed (iz << 16 | ix)
     double *stage;          // [n_src][band_cap]
     int band_cap;
+    int resort_every;       // re-sort the band list along the front every this many rounds (0: never)
     AliSourceRec *rec;      // [n_src]
 };
 
@@ -179,6 +180,16 @@ __device__ __forceinline__ void ali_warp_reserve2(int k, int kw, int *counter, i
 //                survivors into the other buffer, build the next work list and the minimum
 //                of the values that will not be re-evaluated
 //             -- barrier --
+// Angular bin of a band node around the source: entries sorted by it are ordered along the
+// front, so the lanes of a warp work on neighbouring nodes and their gathers coalesce.
+#define ALI_SORT_BINS 2048
+__device__ __forceinline__ int ali_sort_bin(unsigned e, int isz, int isx)
+{
+    float a = atan2f((float)(ALI_PACK_Z(e) - isz), (float)(ALI_PACK_X(e) - isx)); // (-pi, pi]
+    int k = (int)((a + 3.14159265f) * (float)(ALI_SORT_BINS / 6.2831853f));
+    return k < 0 ? 0 : (k >= ALI_SORT_BINS ? ALI_SORT_BINS - 1 : k);
+}
+
 template <int NT>
 __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
 {
@@ -191,7 +202,10 @@ __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
     __shared__ unsigned long long s_evalmin[2], s_basemin[2];
     __shared__ int s_overflow;
     __shared__ unsigned long long s_evals, s_fbs;
+    __shared__ int s_bins[ALI_SORT_BINS];
+    __shared__ int s_wsum[32];
     long long cyc[4] = {0, 0, 0, 0};
+    const int isz = (b.sg > 1 ? b.sg : 1) * rec.src_iz, isx = (b.sg > 1 ? b.sg : 1) * rec.src_ix;
 
     AliBandGrid g;
     g.nz = b.nz; g.nx = b.nx;
@@ -296,7 +310,9 @@ __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
             atomicMin(&s_evalmin[cur], (unsigned long long)__double_as_longlong(lmin));
         __syncthreads();
         long long t2 = clock64();
-        // phase C: accept + extend the band; compact survivors; next work list
+        // phase C: accept + extend the band; compact survivors; next work list (deferred to the
+        // re-sort pass on the rounds that re-order the list along the front)
+        const bool resort = b.resort_every > 0 && (rounds % b.resort_every) == 0;
         const unsigned long long tminb = s_evalmin[cur] < s_basemin[cur] ? s_evalmin[cur] : s_basemin[cur];
         const double thr = __longlong_as_double((long long)tminb) + b.delta;
         double bmin = 1e300;
@@ -315,9 +331,11 @@ __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
                     v = 0.0;
                 } else {
                     out[0] = e; k = 1;
-                    const size_t di = ali_dirty_index(g, iz, ix);
-                    if (g.dirty[di]) { g.dirty[di] = 0; kw = 1; }
-                    else bmin = fmin(bmin, v);
+                    if (!resort) {
+                        const size_t di = ali_dirty_index(g, iz, ix);
+                        if (g.dirty[di]) { g.dirty[di] = 0; kw = 1; }
+                        else bmin = fmin(bmin, v);
+                    }
                 }
             }
             int pos, wpos;
@@ -338,11 +356,90 @@ __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
         if ((tid & 31) == 0 && bmin < 1e300)
             atomicMin(&s_basemin[cur ^ 1], (unsigned long long)__double_as_longlong(bmin));
         __syncthreads();
-        if (tid == 0) {
-            long long t3 = clock64();
-            cyc[0] += t1 - t0; cyc[1] += t2 - t1; cyc[2] += t3 - t2;
+        long long t3 = clock64();
+        if (resort && s_count[cur ^ 1] > 64 && !s_overflow) {
+            // counting sort of the new list by angular bin, from the "next" buffers back into the
+            // current ones (free now); then the work list / base minimum on the sorted order
+            const int nn = s_count[cur ^ 1];
+            for (int q = tid; q < ALI_SORT_BINS; q += NT) s_bins[q] = 0;
+            __syncthreads();
+            for (int i = tid; i < nn; i += NT) atomicAdd(&s_bins[ali_sort_bin(nent[i], isz, isx)], 1);
+            __syncthreads();
+            {   // exclusive scan of the bins (ALI_SORT_BINS / NT bins per thread)
+                constexpr int PER = (ALI_SORT_BINS + NT - 1) / NT;
+                int loc[PER];
+                int sum = 0;
+#pragma unroll
+                for (int q = 0; q < PER; q++) {
+                    int idx = tid * PER + q;
+                    loc[q] = idx < ALI_SORT_BINS ? s_bins[idx] : 0;
+                    sum += loc[q];
+                }
+                int incl = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    int v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if ((tid & 31) >= o) incl += v;
+                }
+                if ((tid & 31) == 31) s_wsum[tid >> 5] = incl;
+                __syncthreads();
+                if (tid < 32) {
+                    int w = tid < NT / 32 ? s_wsum[tid] : 0;
+                    int wi = w;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        int v = __shfl_up_sync(0xffffffffu, wi, o);
+                        if (tid >= o) wi += v;
+                    }
+                    s_wsum[tid] = wi - w;
+                }
+                __syncthreads();
+                int run = s_wsum[tid >> 5] + incl - sum;
+#pragma unroll
+                for (int q = 0; q < PER; q++) {
+                    int idx = tid * PER + q;
+                    if (idx < ALI_SORT_BINS) s_bins[idx] = run;
+                    run += loc[q];
+                }
+            }
+            if (tid == 0) { s_nwork[cur] = 0; s_basemin[cur] = ~0ull; }
+            __syncthreads();
+            for (int i = tid; i < nn; i += NT) {
+                const unsigned e = nent[i];
+                const int pos = atomicAdd(&s_bins[ali_sort_bin(e, isz, isx)], 1);
+                ent[pos] = e;
+                val[pos] = nval[i];
+            }
+            __syncthreads();
+            double bm = 1e300;
+            for (int base = 0; base < nn; base += NT) {
+                const int i = base + tid;
+                int kw = 0;
+                if (i < nn) {
+                    const unsigned e = ent[i];
+                    const double v = val[i];
+                    if (v == 0.0) kw = 1;           // new node: no estimate yet
+                    else {
+                        const size_t di = ali_dirty_index(g, ALI_PACK_Z(e), ALI_PACK_X(e));
+                        if (g.dirty[di]) { g.dirty[di] = 0; kw = 1; }
+                        else bm = fmin(bm, v);
+                    }
+                }
+                int wpos = ali_warp_reserve(kw, &s_nwork[cur]);
+                if (kw) wrk[wpos] = (unsigned)i;
+            }
+            for (int o = 16; o > 0; o >>= 1) bm = fmin(bm, __shfl_xor_sync(0xffffffffu, bm, o));
+            if ((tid & 31) == 0 && bm < 1e300)
+                atomicMin(&s_basemin[cur], (unsigned long long)__double_as_longlong(bm));
+            if (tid == 0) { s_count[cur] = nn; s_evalmin[cur] = ~0ull; } // the list stays in the current buffers
+            __syncthreads();
+        } else {
+            cur ^= 1;
         }
-        cur ^= 1;
+        if (tid == 0) {
+            long long t4 = clock64();
+            cyc[0] += t1 - t0; cyc[1] += t2 - t1; cyc[2] += t3 - t2; cyc[3] += t4 - t3;
+        }
     }
     atomicAdd(&s_evals, my_evals);
     atomicAdd(&s_fbs, my_fbs);
@@ -546,10 +643,11 @@ struct alifmm_ctx {
     std::vector<void *> model_allocs;
     double vmax = 0.0;
     // options
-    double delta_frac = 0.25;
+    double delta_frac = 0.4;
     int margin = 27;
     double band_cap_factor = 6.0;
     int threads_per_source = 1024;
+    int resort_every = 8;
     int band_smem_bytes = 0;   // measured on B200: L1 for the T / status gathers is worth more than smem lists
     // resident batch
     int n_slots = 0, sg = 0, fz = 0, fx = 0;
@@ -712,6 +810,9 @@ extern "C" int alifmm_set_option(alifmm_ctx *c, const char *name, double value)
         int t = (int)value;
         if (t != 256 && t != 512 && t != 1024) return fail(ALIFMM_E_INVALID, "threads_per_source must be 256, 512 or 1024");
         c->threads_per_source = t;
+    } else if (!strcmp(name, "resort_every")) {
+        if (value < 0 || value > 1000000) return fail(ALIFMM_E_INVALID, "resort_every must be >= 0");
+        c->resort_every = (int)value;
     } else if (!strcmp(name, "band_smem_kb")) {
         if (value < 0 || value > 200) return fail(ALIFMM_E_INVALID, "band_smem_kb must be in [0, 200]");
         c->band_smem_bytes = (int)value * 1024;
@@ -775,6 +876,7 @@ static int ttf_attempt(alifmm_ctx *c, int32_t n_src, const int32_t *src_iz, cons
     b.band_cap = (int)(c->band_cap_factor * (double)(fz + fx)) + 1024;
     if (band_cap_override > 0 && band_cap_override < b.band_cap) b.band_cap = band_cap_override;
     *band_overflow = 0;
+    b.resort_every = c->resort_every;
     int rc;
     if ((rc = dev_reserve(c->T, (size_t)n_src * N * sizeof(double))) != 0) return rc;
     if ((rc = dev_reserve(c->st, (size_t)n_src * N + 16)) != 0) return rc;
@@ -857,9 +959,9 @@ static int ttf_attempt(alifmm_ctx *c, int32_t n_src, const int32_t *src_iz, cons
     }
     if (getenv("ALIFMM_DEBUG")) {
         const AliSourceRec &r = recs[0];
-        fprintf(stderr, "[alifmm] source 0: rounds %lld, cycles/round A %.0f B %.0f C %.0f, evals/round %.0f, band max %lld\n",
+        fprintf(stderr, "[alifmm] source 0: rounds %lld, cycles/round A %.0f B %.0f C %.0f sort %.0f, evals/round %.0f, band max %lld\n",
                 r.rounds, (double)r.cycles[0] / (r.rounds + 1e-9), (double)r.cycles[1] / (r.rounds + 1e-9),
-                (double)r.cycles[2] / (r.rounds + 1e-9),
+                (double)r.cycles[2] / (r.rounds + 1e-9), (double)r.cycles[3] / (r.rounds + 1e-9),
                 (double)r.band_evals / (r.rounds + 1e-9), r.max_band);
     }
     if (overflow & 2) *band_overflow = 1;

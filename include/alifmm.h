@@ -79,12 +79,13 @@ int alifmm_device_count(void);
 int alifmm_create(const alifmm_model_desc *desc, int device, alifmm_ctx **out);
 void alifmm_destroy(alifmm_ctx *ctx);
 
-/* Options: "delta_frac" (acceptance band as a fraction of dnx/vmax, default 0.25, must
- * be <= 0.4), "handover_margin" (nodes the sequential replica runs past the last
+/* Options: "delta_frac" (acceptance band as a fraction of dnx/vmax, default and maximum
+ * 0.4: 0.5 changes the solution), "handover_margin" (nodes the sequential replica runs past the last
  * refined source box, default 27), "band_capacity_factor" (narrow-band list capacity as
  * a multiple of nz+nx of the solved grid, default 6), "threads_per_source" (CTA size of
  * the band march: 256, 512 or 1024, default 1024), "band_smem_kb" (shared memory for the
- * band lists, default 0 = keep L1 for the field gathers). */
+ * band lists, default 0 = keep L1 for the field gathers), "resort_every" (re-order the band
+ * list along the front every this many rounds so that warps coalesce, default 8; 0 = never). */
 int alifmm_set_option(alifmm_ctx *ctx, const char *name, double value);
 
 /* Runs the library's kernels on the caller's CUDA stream (a cudaStream_t passed as

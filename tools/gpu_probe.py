@@ -18,6 +18,7 @@ ap.add_argument("--check", type=int, default=1, help="number of fields compared 
 ap.add_argument("--rays", type=int, default=0)
 ap.add_argument("--reps", type=int, default=1)
 ap.add_argument("--smemkb", type=int, default=-1)
+ap.add_argument("--resort", type=int, default=-1)
 a = ap.parse_args()
 
 w = models.weld()
@@ -31,6 +32,7 @@ t0 = time.time()
 ctx = _capi.Context(w["veln"], w["velpn"], w["vel_map"], w["stif_den"], True, g, g.copy(), w["dnx"])
 ctx.set_option("delta_frac", a.frac); ctx.set_option("handover_margin", a.margin); ctx.set_option("threads_per_source", a.threads)
 if a.smemkb >= 0: ctx.set_option("band_smem_kb", a.smemkb)
+if a.resort >= 0: ctx.set_option("resort_every", a.resort)
 print("create %.3f s, mem" % (time.time() - t0), ctx.mem_info())
 for rep in range(a.reps):
     t0 = time.time()
