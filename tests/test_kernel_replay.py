@@ -25,7 +25,7 @@ def test_replay_notebook_gradient_exact(src):
     ref = orc.travel(om, m["dnx"] * src[0], m["dnx"] * src[1], m["dnx"])
     T, cnt, rc = emu.ttf(om, m["dnx"], src[1], src[0], 1)
     assert rc == 0 and cnt["overflow"] == 0
-    assert models.rel_err(ref, T).max() <= 1e-12
+    assert models.rel_err(ref, T).max() <= 1e-11
     assert cnt["band_evals"] < 4.2 * T.size  # dirty tracking keeps evaluations bounded
 
 
@@ -36,7 +36,7 @@ def test_replay_notebook_christoffel_exact(src):
     ref = orc.travel(om, m["dnx"] * src[0], m["dnx"] * src[1], m["dnx"])
     T, cnt, rc = emu.ttf(om, m["dnx"], src[1], src[0], 1)
     assert rc == 0
-    assert models.rel_err(ref, T).max() <= 1e-12
+    assert models.rel_err(ref, T).max() <= 1e-11
 
 
 @pytest.mark.parametrize("src", [(25, 0), (250, 0), (160, 423)])
@@ -46,7 +46,7 @@ def test_replay_weld_coarse_exact(src):
     ref = orc.travel(om, w["dnx"] * src[0], w["dnx"] * src[1], w["dnx"])
     T, cnt, rc = emu.ttf(om, w["dnx"], src[1], src[0], 1)
     assert rc == 0
-    assert models.rel_err(ref, T).max() <= 1e-12
+    assert models.rel_err(ref, T).max() <= 1e-11
 
 
 @pytest.mark.parametrize("sg,src", [(3, (10, 0)), (3, (70, 59)), (3, (40, 30)), (5, (40, 30)), (9, (10, 0))])
@@ -56,7 +56,7 @@ def test_replay_weld_crop_fine_exact(sg, src):
     ref = orc.travel_finer_grid(om, c["dnx"] * src[0], c["dnx"] * src[1], c["dnx"], sg)
     T, cnt, rc = emu.ttf(om, c["dnx"], src[1], src[0], sg)
     assert rc == 0
-    assert models.rel_err(ref, T).max() <= 1e-12
+    assert models.rel_err(ref, T).max() <= 1e-11
 
 
 def test_replay_eager_equals_dirty_tracking():
