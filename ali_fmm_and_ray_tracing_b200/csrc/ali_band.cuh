@@ -79,22 +79,21 @@ ALI_DEV void ali_band_gather(const AliBandGrid &g, int iz, int ix, AliWindow &w)
     }
 }
 
-// FD fallback of a band node, out of line and with by-value arguments so that the hot
-// path keeps its state in registers.  m_dev points to the model struct in device memory.
-ALI_DEV_NOINLINE double ali_band_fouds_slow(const AliModel *m_dev, double *T, uint8_t *st, int nz, int nx, int sg,
-                                            double dnx, int iz, int ix)
+// FD fallback of a band node, out of line and through pointers so that the hot path keeps
+// its state in registers.  m_dev / g_mem point to copies of the model / grid structs in
+// memory (device global resp. shared).
+ALI_DEV_NOINLINE double ali_band_fouds_slow(const AliModel *m_dev, const AliBandGrid *g_mem, int iz, int ix)
 {
     AliModel m = *m_dev;
-    AliBandGrid g;
-    g.nz = nz; g.nx = nx; g.T = T; g.st = st; g.dirty = nullptr; g.tiles_x = 0; g.mv = ali_band_view(sg); g.dnx = dnx;
+    AliBandGrid g = *g_mem;
     AliMat mat;
     ali_fetch_mat(m, g.mv, iz, ix, mat);
-    return ali_fouds18(m, mat, g, iz, ix, dnx, dnx, nx, nz);
+    return ali_fouds18(m, mat, g, iz, ix, g.dnx, g.dnx, g.nx, g.nz);
 }
 
 // Phase A: value the reference would store for this node given the current state.
-ALI_DEV double ali_band_eval(const AliModel &m, const AliModel *m_dev, const AliBandGrid &g, int sg, int iz, int ix,
-                             int *fallback)
+ALI_DEV double ali_band_eval(const AliModel &m, const AliModel *m_dev, const AliBandGrid &g,
+                             const AliBandGrid *g_mem, int iz, int ix, int *fallback)
 {
     AliMat mat;
     AliWindow w;
@@ -102,7 +101,7 @@ ALI_DEV double ali_band_eval(const AliModel &m, const AliModel *m_dev, const Ali
     ali_band_gather(g, iz, ix, w);
     double v = ali_update_window(m, mat, w, iz, ix, g.nz, g.nx, g.dnx, nullptr);
     if (v == -1.0) {
-        v = ali_band_fouds_slow(m_dev, g.T, g.st, g.nz, g.nx, sg, g.dnx, iz, ix);
+        v = ali_band_fouds_slow(m_dev, g_mem, iz, ix);
         *fallback = 1;
     }
     return v;
@@ -189,4 +188,26 @@ ALI_DEV double ali_node_vmax(const AliModel &m, int iz, int ix)
         }
     }
     return best;
+}
+
+// ---------------------------------------------------------------------------
+// Hybrid source levels: a refined level grid can be marched by band rounds too, between a
+// sequential warm-up (ali_seq.cuh) and the moment its front leaves the refined box.
+// ---------------------------------------------------------------------------
+// Box edges whose crossing ends a level (the edges the domain did not clip; ATR:1651-1652,
+// 1673-1674): bit 0 left (x = 0), 1 right, 2 top (z = 0), 3 bottom.
+ALI_HD int ali_level_stop_mask(int nz, int nx, int cz, int cx, int max_dist)
+{
+    int mask = 0;
+    if (cx == max_dist) mask |= 1;
+    if (nx - 1 - cx == max_dist) mask |= 2;
+    if (cz == max_dist) mask |= 4;
+    if (nz - 1 - cz == max_dist) mask |= 8;
+    return mask;
+}
+
+ALI_DEV bool ali_level_on_stop_edge(int mask, int nz, int nx, int iz, int ix)
+{
+    return ((mask & 1) && ix == 0) || ((mask & 2) && ix == nx - 1) || ((mask & 4) && iz == 0) ||
+           ((mask & 8) && iz == nz - 1);
 }

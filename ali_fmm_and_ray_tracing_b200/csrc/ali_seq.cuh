@@ -129,7 +129,14 @@ ALI_DEV void ali_downtree(AliSeqGrid &g)
 
 struct AliSeqCounters {
     long long pops, evals, fallbacks;
+    long long cyc_heap, cyc_eval;   // device builds: SM cycles in heap operations / evaluations
 };
+
+#if defined(__CUDA_ARCH__)
+#define ALI_CLOCK() clock64()
+#else
+#define ALI_CLOCK() 0ll
+#endif
 
 // One heap-ordered march (ATR:1621-1674 and its copies ATR:1787-1844, 1937-1993,
 // 2055-2102, 2292-2346, 2460-2504, 2775-2817).
@@ -139,47 +146,62 @@ struct AliSeqCounters {
 //                   close nodes (ATR:1645);
 //   stop_r >= 0   : (main grid only) stop after popping a node whose Chebyshev distance
 //                   from the centre reaches stop_r -- hand-over point to the band march.
-ALI_DEV void ali_seq_march(AliSeqGrid &g, const AliModel &m, int cx, int cz, int max_dist, int nnz_bug, int stop_r,
-                           AliSeqCounters &cnt)
+// Returns why it stopped: 0 heap empty, 1 front left the refined box, 2 stop_r reached,
+// 3 scratch exhausted / window too small.
+#define ALI_SEQ_EMPTY 0
+#define ALI_SEQ_BOX 1
+#define ALI_SEQ_HANDOVER 2
+#define ALI_SEQ_LIMIT 3
+ALI_DEV int ali_seq_march(AliSeqGrid &g, const AliModel &m, int cx, int cz, int max_dist, int nnz_bug, int stop_r,
+                          AliSeqCounters &cnt)
 {
     bool finished = false;
+    int why = ALI_SEQ_EMPTY;
     const int nnx = g.nx, nnz = g.nz;
     while (g.ntr > 0 && !finished) {
         const int ix = g.heap[3], iz = g.heap[2];
+        long long c0 = ALI_CLOCK();
         g.s(iz, ix) = 0;
         ali_downtree(g);
         cnt.pops++;
+        cnt.cyc_heap += ALI_CLOCK() - c0;
         for (int s = 0; s < 4; s++) {
             int z = iz, x = ix;
             if (s == 0) x = ix - 1; else if (s == 1) x = ix + 1; else if (s == 2) z = iz - 1; else z = iz + 1;
             bool inside = (s < 2) ? (0 <= x && x <= nnx - 1) : (0 <= z && z <= nnz - 1);
             if (inside) {
-                if (!g.in_win(z, x)) { finished = true; continue; } // window too small: hand over early
+                if (!g.in_win(z, x)) { finished = true; why = ALI_SEQ_LIMIT; continue; } // window too small: hand over early
                 int32_t stv = g.s(z, x);
                 if (stv != 0) {
                     int nnz_l = (nnz_bug && s < 2 && stv > 0) ? nnx : nnz;
                     int fb = 0;
+                    long long c1 = ALI_CLOCK();
                     double v = ali_eval_node(m, g.mv, g, z, x, nnz_l, nnx, nnz, nnx, g.dnx, &fb);
+                    long long c2 = ALI_CLOCK();
                     cnt.evals++;
                     cnt.fallbacks += fb;
                     g.tref(z, x) = v;
                     if (stv == -1) ali_addtree(g, z, x);
                     else ali_updtree(g, z, x);
+                    cnt.cyc_eval += c2 - c1;
+                    cnt.cyc_heap += ALI_CLOCK() - c2;
                 }
             } else if (max_dist >= 0) {
                 int d = (s < 2) ? (cx - x) : (cz - z);
                 if (d < 0) d = -d;
-                if (d == max_dist + 1) finished = true;
+                if (d == max_dist + 1) { finished = true; why = ALI_SEQ_BOX; }
             }
         }
-        if (stop_r >= 0) {
+        if (stop_r >= 0 && why != ALI_SEQ_BOX) {
             int dz = iz - cz, dx = ix - cx;
             if (dz < 0) dz = -dz;
             if (dx < 0) dx = -dx;
-            if ((dz > dx ? dz : dx) >= stop_r) finished = true;
+            if ((dz > dx ? dz : dx) >= stop_r) { finished = true; if (why == ALI_SEQ_EMPTY) why = ALI_SEQ_HANDOVER; }
         }
-        if (g.overflow) finished = true;
+        if (g.overflow) { finished = true; why = ALI_SEQ_LIMIT; }
     }
+    if (!finished) why = ALI_SEQ_EMPTY;
+    return why;
 }
 
 // Resets a level grid: T = 0, status = far.  Cooperative over `nlanes` lanes.
@@ -322,55 +344,95 @@ struct AliSeqResult {
     AliSeqCounters cnt;
 };
 
-// Runs levels + main-grid sequential march for one source.  `T` is the source's main-grid
-// field (zero-filled by the caller).  Lanes other than 0 only take part in the fills.
-ALI_DEV void ali_seq_source(const AliModel &m, const AliSourcePlan &p, const AliSeqScratch &sc, double *T,
-                            AliSeqResult &res, int lane, int nlanes)
-{
+// ---------------------------------------------------------------------------
+// One source, step by step.  The driver (ali_seq_source below for the all-sequential form,
+// the ttf kernel / host replay for the hybrid form) calls, per level:
+//   ali_src_level_geometry   every lane: extents, buffers, view of level l
+//   ali_src_level_fill       cooperative: reset + analytic seed (level 0)
+//   ali_src_level_start      one lane: perimeter push (level 0) or hand-off from level l-1
+//   ali_src_level_seq        one lane: heap-ordered march, optionally only up to stop_r
+// and the same four for the main grid.
+// ---------------------------------------------------------------------------
+struct AliSrcState {
     AliSeqGrid lv[2];
-    int cz[2] = {0, 0}, cx[2] = {0, 0};
-    AliSeqCounters cnt;
-    cnt.pops = cnt.evals = cnt.fallbacks = 0;
-    int overflow = 0;
-    // view of the grid the levels refine: the coarse model (travel) or the sg-refined one
-    const AliMatView base = ali_make_view(1, 0, 0, p.fine ? p.sg : 1, p.fine ? 1 : 0);
-
-    for (int l = 0; l < p.nlev; l++) {
-        const int cur = l & 1;
-        AliSeqGrid &g = lv[cur];
-        const int size = p.size[l], scl = p.scale[l];
-        const int left = ali_imax(0, p.isx - size), right = ali_imin(p.nx - 1, p.isx + size);
-        const int bottom = ali_imax(0, p.isz - size), top = ali_imin(p.nz - 1, p.isz + size);
-        g.nz = scl * (top - bottom) + 1;
-        g.nx = scl * (right - left) + 1;
-        g.t = cur == 0 ? sc.tA : sc.tB;
-        g.st = cur == 0 ? sc.sA : sc.sB;
-        g.t_stride = g.nx;
-        g.wz0 = 0; g.wx0 = 0; g.wnz = g.nz; g.wnx = g.nx;
-        g.heap = sc.heap; g.heap_cap = sc.heap_cap;
-        g.mv = ali_make_view(scl, bottom, left, p.fine ? p.sg : 1, 1);
-        g.dnx = m.dnx / scl;
-        cx[cur] = scl * (p.isx - left);
-        cz[cur] = scl * (p.isz - bottom);
-        ali_seq_clear(g, true, lane, nlanes);
-        ALI_SYNCWARP();
-        if (l == 0) {
-            const int side1 = p.fine ? (4 + 9 * ((p.sg - 1) / 2)) : 13;
-            ali_seq_seed(g, m, base, p.isz, p.isx, cz[cur], cx[cur], side1, p.fine ? 1.0 : -1.0, lane, nlanes);
-            ALI_SYNCWARP();
-            if (lane == 0) ali_seq_seed_push(g, cz[cur], cx[cur], side1);
-        } else if (lane == 0) {
-            ali_seq_handoff(lv[cur ^ 1], cz[cur ^ 1], cx[cur ^ 1], g, cz[cur], cx[cur]);
-        }
-        if (lane == 0) {
-            ali_seq_march(g, m, cx[cur], cz[cur], scl * size, (!p.fine && l == 0) ? 1 : 0, -1, cnt);
-            overflow |= g.overflow;
-        }
-        ALI_SYNCWARP();
-    }
-
-    // main grid: statuses in a window around the source, T in the caller's field
     AliSeqGrid mg;
+    int cz[2], cx[2];
+    AliSeqCounters cnt;
+    int overflow;
+    AliMatView base;   // view of the grid the levels refine: the coarse model (travel) or the sg-refined one
+};
+
+ALI_DEV void ali_src_begin(AliSrcState &s, const AliSourcePlan &p)
+{
+    s.cz[0] = s.cz[1] = s.cx[0] = s.cx[1] = 0;
+    s.cnt.pops = s.cnt.evals = s.cnt.fallbacks = 0;
+    s.cnt.cyc_heap = s.cnt.cyc_eval = 0;
+    s.overflow = 0;
+    s.base = ali_make_view(1, 0, 0, p.fine ? p.sg : 1, p.fine ? 1 : 0);
+}
+
+ALI_DEV void ali_src_level_geometry(AliSrcState &s, const AliModel &m, const AliSourcePlan &p,
+                                    const AliSeqScratch &sc, int l)
+{
+    const int cur = l & 1;
+    AliSeqGrid &g = s.lv[cur];
+    const int size = p.size[l], scl = p.scale[l];
+    const int left = ali_imax(0, p.isx - size), right = ali_imin(p.nx - 1, p.isx + size);
+    const int bottom = ali_imax(0, p.isz - size), top = ali_imin(p.nz - 1, p.isz + size);
+    g.nz = scl * (top - bottom) + 1;
+    g.nx = scl * (right - left) + 1;
+    g.t = cur == 0 ? sc.tA : sc.tB;
+    g.st = cur == 0 ? sc.sA : sc.sB;
+    g.t_stride = g.nx;
+    g.wz0 = 0; g.wx0 = 0; g.wnz = g.nz; g.wnx = g.nx;
+    g.heap = sc.heap; g.heap_cap = sc.heap_cap;
+    g.mv = ali_make_view(scl, bottom, left, p.fine ? p.sg : 1, 1);
+    g.dnx = m.dnx / scl;
+    s.cx[cur] = scl * (p.isx - left);
+    s.cz[cur] = scl * (p.isz - bottom);
+}
+
+// Half-side of the level's initial alive square: the analytic seed on level 0, the previous
+// level's box (in this level's nodes) otherwise.
+ALI_HD int ali_src_level_ring(const AliSourcePlan &p, int l)
+{
+    if (l == 0) return p.fine ? (4 + 9 * ((p.sg - 1) / 2)) : 13;
+    return p.scale[l] * p.size[l - 1];
+}
+
+ALI_DEV void ali_src_level_fill(AliSrcState &s, const AliModel &m, const AliSourcePlan &p, int l, int lane,
+                                int nlanes, bool sync_between)
+{
+    const int cur = l & 1;
+    AliSeqGrid &g = s.lv[cur];
+    ali_seq_clear(g, true, lane, nlanes);
+    if (l == 0) {
+        if (sync_between) ALI_SYNCWARP();
+        ali_seq_seed(g, m, s.base, p.isz, p.isx, s.cz[cur], s.cx[cur], ali_src_level_ring(p, 0),
+                     p.fine ? 1.0 : -1.0, lane, nlanes);
+    }
+}
+
+ALI_DEV void ali_src_level_start(AliSrcState &s, const AliSourcePlan &p, int l)
+{
+    const int cur = l & 1;
+    if (l == 0) ali_seq_seed_push(s.lv[cur], s.cz[cur], s.cx[cur], ali_src_level_ring(p, 0));
+    else ali_seq_handoff(s.lv[cur ^ 1], s.cz[cur ^ 1], s.cx[cur ^ 1], s.lv[cur], s.cz[cur], s.cx[cur]);
+}
+
+ALI_DEV int ali_src_level_seq(AliSrcState &s, const AliModel &m, const AliSourcePlan &p, int l, int stop_r)
+{
+    const int cur = l & 1;
+    int why = ali_seq_march(s.lv[cur], m, s.cx[cur], s.cz[cur], p.scale[l] * p.size[l],
+                            (!p.fine && l == 0) ? 1 : 0, stop_r, s.cnt);
+    s.overflow |= s.lv[cur].overflow;
+    return why;
+}
+
+ALI_DEV void ali_src_main_geometry(AliSrcState &s, const AliModel &m, const AliSourcePlan &p, const AliSeqScratch &sc,
+                                   double *T)
+{
+    AliSeqGrid &mg = s.mg;
     const int last = (p.nlev - 1) & 1;
     const int half = p.stop_r + 4;
     mg.nz = p.nz; mg.nx = p.nx;
@@ -380,20 +442,44 @@ ALI_DEV void ali_seq_source(const AliModel &m, const AliSourcePlan &p, const Ali
     mg.wnz = ali_imin(p.nz - 1, p.isz + half) - mg.wz0 + 1;
     mg.wnx = ali_imin(p.nx - 1, p.isx + half) - mg.wx0 + 1;
     mg.heap = sc.heap; mg.heap_cap = sc.heap_cap;
-    mg.mv = base;
+    mg.mv = s.base;
     mg.dnx = m.dnx;
-    if ((size_t)mg.wnz * mg.wnx > sc.status_cap) overflow = 1;
-    if (!overflow) {
-        ali_seq_clear(mg, false, lane, nlanes);
+    if ((size_t)mg.wnz * mg.wnx > sc.status_cap) s.overflow = 1;
+}
+
+ALI_DEV void ali_src_main_start_and_seq(AliSrcState &s, const AliModel &m, const AliSourcePlan &p)
+{
+    const int last = (p.nlev - 1) & 1;
+    ali_seq_handoff(s.lv[last], s.cz[last], s.cx[last], s.mg, p.isz, p.isx);
+    ali_seq_march(s.mg, m, p.isx, p.isz, -1, 0, p.stop_r, s.cnt);
+    s.overflow |= s.mg.overflow;
+}
+
+// All-sequential form: levels + main-grid start for one source.  `T` is the source's main-grid
+// field.  Lanes other than 0 only take part in the fills.
+ALI_DEV void ali_seq_source(const AliModel &m, const AliSourcePlan &p, const AliSeqScratch &sc, double *T,
+                            AliSeqResult &res, int lane, int nlanes)
+{
+    AliSrcState s;
+    ali_src_begin(s, p);
+    for (int l = 0; l < p.nlev; l++) {
+        ali_src_level_geometry(s, m, p, sc, l);
+        ali_src_level_fill(s, m, p, l, lane, nlanes, true);
         ALI_SYNCWARP();
         if (lane == 0) {
-            ali_seq_handoff(lv[last], cz[last], cx[last], mg, p.isz, p.isx);
-            ali_seq_march(mg, m, p.isx, p.isz, -1, 0, p.stop_r, cnt);
-            overflow |= mg.overflow;
+            ali_src_level_start(s, p, l);
+            ali_src_level_seq(s, m, p, l, -1);
         }
         ALI_SYNCWARP();
     }
-    res.wz0 = mg.wz0; res.wx0 = mg.wx0; res.wnz = mg.wnz; res.wnx = mg.wnx;
-    res.overflow = overflow;
-    res.cnt = cnt;
+    ali_src_main_geometry(s, m, p, sc, T);
+    if (!s.overflow) {
+        ali_seq_clear(s.mg, false, lane, nlanes);
+        ALI_SYNCWARP();
+        if (lane == 0) ali_src_main_start_and_seq(s, m, p);
+        ALI_SYNCWARP();
+    }
+    res.wz0 = s.mg.wz0; res.wx0 = s.mg.wx0; res.wnz = s.mg.wnz; res.wnx = s.mg.wnx;
+    res.overflow = s.overflow;
+    res.cnt = s.cnt;
 }

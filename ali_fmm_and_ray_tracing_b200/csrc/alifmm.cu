@@ -202,6 +202,7 @@ __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
     __shared__ unsigned long long s_evalmin[2], s_basemin[2];
     __shared__ int s_overflow;
     __shared__ unsigned long long s_evals, s_fbs;
+    __shared__ AliBandGrid s_grid;   // copy for the out-of-line FD fallback
     __shared__ int s_bins[ALI_SORT_BINS];
     __shared__ int s_wsum[32];
     long long cyc[4] = {0, 0, 0, 0};
@@ -229,6 +230,7 @@ __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
     }
 
     if (tid == 0) {
+        s_grid = g;
         s_count[0] = 0; s_count[1] = 0; s_nwork[0] = 0; s_nwork[1] = 0;
         s_evalmin[0] = ~0ull; s_evalmin[1] = ~0ull; s_basemin[0] = ~0ull; s_basemin[1] = ~0ull;
         s_overflow = rec.overflow;
@@ -288,7 +290,7 @@ __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
             int fb = 0;
             const size_t di = ali_dirty_index(g, iz, ix);
             g.dirty[di] = 0;
-            val[i] = ali_band_eval(b.m, b.m_dev, g, b.sg, iz, ix, &fb);
+            val[i] = ali_band_eval(b.m, b.m_dev, g, &s_grid, iz, ix, &fb);
             if (fb) g.dirty[di] = 1; // the fallback also reads alive flags: always re-evaluate
             my_evals++;
             my_fbs += fb;
@@ -959,6 +961,9 @@ static int ttf_attempt(alifmm_ctx *c, int32_t n_src, const int32_t *src_iz, cons
     }
     if (getenv("ALIFMM_DEBUG")) {
         const AliSourceRec &r = recs[0];
+        fprintf(stderr, "[alifmm] source 0 seq: pops %lld evals %lld, cycles/pop heap %.0f eval %.0f (per eval %.0f)\n", r.seq.cnt.pops,
+                r.seq.cnt.evals, (double)r.seq.cnt.cyc_heap / (r.seq.cnt.pops + 1e-9), (double)r.seq.cnt.cyc_eval / (r.seq.cnt.pops + 1e-9),
+                (double)r.seq.cnt.cyc_eval / (r.seq.cnt.evals + 1e-9));
         fprintf(stderr, "[alifmm] source 0: rounds %lld, cycles/round A %.0f B %.0f C %.0f sort %.0f, evals/round %.0f, band max %lld\n",
                 r.rounds, (double)r.cycles[0] / (r.rounds + 1e-9), (double)r.cycles[1] / (r.rounds + 1e-9),
                 (double)r.cycles[2] / (r.rounds + 1e-9), (double)r.cycles[3] / (r.rounds + 1e-9),

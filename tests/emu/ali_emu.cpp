@@ -101,12 +101,101 @@ extern "C" double emu_model_vmax(int nz, int nx, const double *veln, const int32
     return best;
 }
 
+// Band rounds on one grid (host replay of the kernel's round loop).
+//   stop_mask != 0: a refined level -- end when the first node on an unclipped box edge is
+//   accepted (ATR:1651-1652), accepting only nodes up to that node's time in the last round and
+//   evaluating the nodes that round enlisted.
+struct BandStats { long long rounds = 0, evals = 0, fbs = 0, maxlist = 0; };
+
+static void band_run(const AliModel &m, AliBandGrid &bg, std::vector<unsigned> &list, double delta, int stop_mask,
+                     bool eager, BandStats &st)
+{
+    std::vector<unsigned> next;
+    std::vector<double> tnew;
+    bool last_round = false;
+    while (!list.empty()) {
+        st.rounds++;
+        if ((long long)list.size() > st.maxlist) st.maxlist = (long long)list.size();
+        tnew.resize(list.size());
+        for (size_t i = 0; i < list.size(); i++) {
+            const int iz = ALI_PACK_Z(list[i]), ix = ALI_PACK_X(list[i]);
+            const size_t node = (size_t)iz * bg.nx + ix;
+            const size_t di = ali_dirty_index(bg, iz, ix);
+            if (bg.dirty[di] || eager) {
+                int fb = 0;
+                bg.dirty[di] = 0;
+                tnew[i] = ali_band_eval(m, &m, bg, &bg, iz, ix, &fb);
+                if (fb) bg.dirty[di] = 1;
+                st.evals++; st.fbs += fb;
+            } else {
+                tnew[i] = bg.T[node];
+            }
+        }
+        double tmin = 1e300;
+        for (size_t i = 0; i < list.size(); i++) {
+            ali_band_publish(bg, ALI_PACK_Z(list[i]), ALI_PACK_X(list[i]), tnew[i]);
+            if (tnew[i] < tmin) tmin = tnew[i];
+        }
+        if (last_round) break;   // the extra evaluation round after the stop
+        double thr = tmin + delta;
+        if (stop_mask) {
+            double tstar = 1e300;
+            for (size_t i = 0; i < list.size(); i++)
+                if (tnew[i] <= thr && ali_level_on_stop_edge(stop_mask, bg.nz, bg.nx, ALI_PACK_Z(list[i]), ALI_PACK_X(list[i])) &&
+                    tnew[i] < tstar)
+                    tstar = tnew[i];
+            if (tstar < 1e300) { thr = tstar; last_round = true; }
+        }
+        next.clear();
+        for (size_t i = 0; i < list.size(); i++) {
+            if (tnew[i] <= thr) {
+                unsigned nb[4];
+                int cnt = ali_band_accept(bg, ALI_PACK_Z(list[i]), ALI_PACK_X(list[i]), nb);
+                for (int k = 0; k < cnt; k++) {
+                    next.push_back(nb[k]);   // new nodes are always evaluated next round (kernel: work list)
+                    bg.dirty[ali_dirty_index(bg, ALI_PACK_Z(nb[k]), ALI_PACK_X(nb[k]))] = 1;
+                }
+            } else {
+                next.push_back(list[i]);
+            }
+        }
+        list.swap(next);
+    }
+}
+
+// Sequential state of a grid window -> band representation (far = NaN bits, alive byte, list).
+static void seq_to_band(const AliSeqGrid &g, AliBandGrid &bg, std::vector<unsigned> &list)
+{
+    for (int z = 0; z < g.wnz; z++)
+        for (int x = 0; x < g.wnx; x++) {
+            int32_t s = g.st[(size_t)z * g.wnx + x];
+            const int az = g.wz0 + z, ax = g.wx0 + x;
+            size_t node = (size_t)az * bg.nx + ax;
+            if (s == 0) bg.st[node] = ALI_ST_ALIVE;
+            else if (s > 0) { list.push_back(ALI_PACK(az, ax)); bg.dirty[ali_dirty_index(bg, az, ax)] = 1; }
+            else { unsigned long long bits = ALI_T_FAR_BITS; std::memcpy(&bg.T[node], &bits, 8); }
+        }
+}
+
+// Band representation of a level -> sequential statuses for the hand-off (-1 far, 0 alive, 1 band).
+static void band_to_seq(const AliBandGrid &bg, AliSeqGrid &g)
+{
+    for (int z = 0; z < g.nz; z++)
+        for (int x = 0; x < g.nx; x++) {
+            size_t node = (size_t)z * g.nx + x;
+            if (bg.st[node] == ALI_ST_ALIVE) g.st[node] = 0;
+            else if (bg.T[node] >= 0.0) g.st[node] = 1;
+            else g.st[node] = -1;
+        }
+}
+
 // counters: [0] seq pops, [1] seq evals, [2] seq fallbacks, [3] band rounds, [4] band evals,
-//           [5] band fallbacks, [6] max list length, [7] overflow flag
+//           [5] band fallbacks, [6] max list length, [7] overflow flag, [8] level band rounds,
+//           [9] level band evals
 extern "C" int emu_ttf(int nz, int nx, const double *veln, const int32_t *velpn, const double *vel_map,
                        const long long *stif, int has_stif, const double *group_tab, const double *phase_tab,
-                       int ncol, double dnx, int src_iz, int src_ix, int sg, int margin, double delta, int eager,
-                       double *T, long long *counters)
+                       int ncol, double dnx, int src_iz, int src_ix, int sg, int margin, double delta_frac,
+                       double vmax, int eager, int level_margin, double *T, long long *counters)
 {
     HostModel hm;
     make_model(hm, nz, nx, veln, velpn, vel_map, stif, has_stif, group_tab, phase_tab, ncol, dnx);
@@ -123,72 +212,65 @@ extern "C" int emu_ttf(int nz, int nx, const double *veln, const int32_t *velpn,
     sc.tA = tA.data(); sc.tB = tB.data(); sc.sA = sA.data(); sc.sB = sB.data();
     sc.heap = heap.data(); sc.heap_cap = (int)(cap / 2 + 64); sc.status_cap = cap;
     std::memset(T, ALI_T_UNSET_BYTE, n * sizeof(double)); // NaN = no estimate
-    AliSeqResult res;
-    ali_seq_source(m, p, sc, T, res, 0, 1);
-    counters[0] = res.cnt.pops; counters[1] = res.cnt.evals; counters[2] = res.cnt.fallbacks;
-    counters[7] = res.overflow;
-    if (res.overflow) return -1;
+    const double delta = delta_frac * dnx / vmax;   // the levels scale it with their spacing
 
-    // ---- band-synchronous march (replay of ali_march_kernel) ----
-    std::vector<uint8_t> status(n, ALI_ST_FAR), dirty(ali_dirty_bytes(p.nz, p.nx), 0);
-    std::vector<unsigned> list, next;
-    const int32_t *wst = ((p.nlev - 1) & 1) == 0 ? sc.sB : sc.sA;
-    for (int z = 0; z < res.wnz; z++)
-        for (int x = 0; x < res.wnx; x++) {
-            int32_t s = wst[(size_t)z * res.wnx + x];
-            size_t node = (size_t)(res.wz0 + z) * p.nx + (res.wx0 + x);
-            if (s == 0) status[node] = ALI_ST_ALIVE;
-            else if (s > 0) { list.push_back(ALI_PACK(res.wz0 + z, res.wx0 + x)); }
-            else { unsigned long long bits = ALI_T_FAR_BITS; std::memcpy(&T[node], &bits, 8); }
+    AliSrcState s;
+    ali_src_begin(s, p);
+    BandStats lst, mst;
+    std::vector<uint8_t> lalive(lvl), ldirty(ali_dirty_bytes(2 * 4096, 2 * 4096) > 0 ? 0 : 0);
+    for (int l = 0; l < p.nlev; l++) {
+        ali_src_level_geometry(s, m, p, sc, l);
+        ali_src_level_fill(s, m, p, l, 0, 1, false);
+        ali_src_level_start(s, p, l);
+        AliSeqGrid &g = s.lv[l & 1];
+        const int ring = ali_src_level_ring(p, l);
+        const int stop_r = level_margin >= 0 ? ring + level_margin : -1;
+        int why = ali_src_level_seq(s, m, p, l, stop_r);
+        if (why == ALI_SEQ_HANDOVER) {
+            // band rounds on the level grid until the front leaves the refined box
+            AliBandGrid bg;
+            bg.nz = g.nz; bg.nx = g.nx; bg.T = g.t; bg.dnx = g.dnx; bg.mv = g.mv;
+            std::fill(lalive.begin(), lalive.begin() + (size_t)g.nz * g.nx, (uint8_t)ALI_ST_FAR);
+            ldirty.assign(ali_dirty_bytes(g.nz, g.nx), 0);
+            bg.st = lalive.data(); bg.dirty = ldirty.data(); bg.tiles_x = ali_dirty_tiles_x(g.nx);
+            std::vector<unsigned> list;
+            seq_to_band(g, bg, list);
+            int mask = ali_level_stop_mask(g.nz, g.nx, s.cz[l & 1], s.cx[l & 1], p.scale[l] * p.size[l]);
+            band_run(m, bg, list, delta / p.scale[l], mask, eager != 0, lst);
+            band_to_seq(bg, g);
         }
+        if (const char *dbg = getenv("ALI_EMU_DUMP")) {
+            char fn[256];
+            snprintf(fn, sizeof fn, "%s_L%d.bin", dbg, l);
+            FILE *f = fopen(fn, "wb");
+            int hdr[4] = {g.nz, g.nx, s.cz[l & 1], s.cx[l & 1]};
+            fwrite(hdr, 4, 4, f);
+            fwrite(g.t, 8, (size_t)g.nz * g.nx, f);
+            fwrite(g.st, 4, (size_t)g.nz * g.nx, f);
+            fclose(f);
+        }
+    }
+    ali_src_main_geometry(s, m, p, sc, T);
+    counters[7] = s.overflow;
+    if (s.overflow) return -1;
+    ali_seq_clear(s.mg, false, 0, 1);
+    ali_src_main_start_and_seq(s, m, p);
+    counters[0] = s.cnt.pops; counters[1] = s.cnt.evals; counters[2] = s.cnt.fallbacks;
+    counters[7] = s.overflow;
+    if (s.overflow) return -1;
+
+    // ---- band-synchronous march of the main grid (replay of the kernel's round loop) ----
+    std::vector<uint8_t> status(n, ALI_ST_FAR), dirty(ali_dirty_bytes(p.nz, p.nx), 0);
     AliBandGrid bg;
     bg.nz = p.nz; bg.nx = p.nx; bg.T = T; bg.st = status.data(); bg.dirty = dirty.data(); bg.dnx = m.dnx;
     bg.tiles_x = ali_dirty_tiles_x(p.nx);
-    for (size_t i = 0; i < list.size(); i++) dirty[ali_dirty_index(bg, ALI_PACK_Z(list[i]), ALI_PACK_X(list[i]))] = 1;
     bg.mv = ali_band_view(sg);
-    std::vector<double> tnew;
-    long long rounds = 0, evals = 0, fbs = 0, maxlist = 0;
-    while (!list.empty()) {
-        rounds++;
-        if ((long long)list.size() > maxlist) maxlist = (long long)list.size();
-        tnew.resize(list.size());
-        for (size_t i = 0; i < list.size(); i++) {
-            const int iz = ALI_PACK_Z(list[i]), ix = ALI_PACK_X(list[i]);
-            const size_t node = (size_t)iz * p.nx + ix;
-            const size_t di = ali_dirty_index(bg, iz, ix);
-            if (dirty[di] || eager) {
-                int fb = 0;
-                dirty[di] = 0;
-                tnew[i] = ali_band_eval(m, &m, bg, sg, iz, ix, &fb);
-                if (fb) dirty[di] = 1;
-                evals++; fbs += fb;
-            } else {
-                tnew[i] = T[node];
-            }
-        }
-        double tmin = 1e300;
-        for (size_t i = 0; i < list.size(); i++) {
-            ali_band_publish(bg, ALI_PACK_Z(list[i]), ALI_PACK_X(list[i]), tnew[i]);
-            if (tnew[i] < tmin) tmin = tnew[i];
-        }
-        const double thr = tmin + delta;
-        next.clear();
-        for (size_t i = 0; i < list.size(); i++) {
-            if (tnew[i] <= thr) {
-                unsigned nb[4];
-                int cnt = ali_band_accept(bg, ALI_PACK_Z(list[i]), ALI_PACK_X(list[i]), nb);
-                for (int k = 0; k < cnt; k++) {
-                    next.push_back(nb[k]);   // new nodes are always evaluated next round (kernel: work list)
-                    dirty[ali_dirty_index(bg, ALI_PACK_Z(nb[k]), ALI_PACK_X(nb[k]))] = 1;
-                }
-            } else {
-                next.push_back(list[i]);
-            }
-        }
-        list.swap(next);
-    }
+    std::vector<unsigned> list;
+    seq_to_band(s.mg, bg, list);
+    band_run(m, bg, list, delta, 0, eager != 0, mst);
     for (size_t i = 0; i < n; i++) T[i] = (T[i] >= 0.0) ? T[i] / p.sg : 0.0; // ATR:2832
-    counters[3] = rounds; counters[4] = evals; counters[5] = fbs; counters[6] = maxlist;
+    counters[3] = mst.rounds; counters[4] = mst.evals; counters[5] = mst.fbs + lst.fbs; counters[6] = mst.maxlist;
+    counters[8] = lst.rounds; counters[9] = lst.evals;
     return 0;
 }
 

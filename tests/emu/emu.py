@@ -40,18 +40,19 @@ def model_vmax(m, dnx):
     return lib().emu_model_vmax(*_margs(m, dnx))
 
 
-def ttf(m, dnx, src_iz, src_ix, sg=1, margin=27, frac=0.4, vmax=None, eager=False):
+def ttf(m, dnx, src_iz, src_ix, sg=1, margin=27, frac=0.4, vmax=None, eager=False, level_margin=-1):
     """Replays seq-init + band march for one source; m is an oracle.ali_oracle.Model."""
     if vmax is None:
         vmax = model_vmax(m, dnx)
-    delta = frac * dnx / vmax
     nz = sg * (m.nz - 1) + 1 if sg > 1 else m.nz
     nx = sg * (m.nx - 1) + 1 if sg > 1 else m.nx
     T = np.zeros((nz, nx))
-    cnt = np.zeros(8, dtype=np.int64)
-    rc = lib().emu_ttf(*_margs(m, dnx), int(src_iz), int(src_ix), int(sg), int(margin), ctypes.c_double(delta),
-                       int(eager), _p(T, _f64p), cnt.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)))
-    names = ["seq_pops", "seq_evals", "seq_fallbacks", "rounds", "band_evals", "band_fallbacks", "max_list", "overflow"]
+    cnt = np.zeros(10, dtype=np.int64)
+    rc = lib().emu_ttf(*_margs(m, dnx), int(src_iz), int(src_ix), int(sg), int(margin), ctypes.c_double(frac),
+                       ctypes.c_double(vmax), int(eager), int(level_margin), _p(T, _f64p),
+                       cnt.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)))
+    names = ["seq_pops", "seq_evals", "seq_fallbacks", "rounds", "band_evals", "band_fallbacks", "max_list", "overflow",
+             "level_rounds", "level_evals"]
     return T, dict(zip(names, cnt.tolist())), rc
 
 
