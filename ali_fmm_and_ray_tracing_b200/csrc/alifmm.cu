@@ -645,7 +645,7 @@ struct alifmm_ctx {
     std::vector<void *> model_allocs;
     double vmax = 0.0;
     // options
-    double delta_frac = 0.4;
+    double delta_frac = 0.3;
     int margin = 27;
     double band_cap_factor = 6.0;
     int threads_per_source = 1024;

@@ -310,12 +310,12 @@ def run_gpu(args):
                 "l2_policy": "inputs_larger_than_l2 (%.1f GB of fields per step)" % (n_src * node_solves_step / n_src * 10 / 1e9),
                 "ms_seq_kernel": statistics.mean(ms_seq), "ms_march_kernel": march_ms, "ms_rays_kernel": statistics.mean(ms_rays),
                 "band_rounds_max": c1["band_rounds_max"], "update_evals_per_node_solve": (c1["band_evals"] + c1["seq_evals"]) / node_solves_step,
-                "fallback_evals": c1["fallback_evals"], "delta_frac": args.delta_frac or 0.4,
+                "fallback_evals": c1["fallback_evals"], "delta_frac": args.delta_frac or 0.3,
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "ali_march_kernel", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": node_solves_step * B_ALG,
-                         "note": "the march is round-latency bound (one barrier-separated round per 0.4 dnx/vmax of "
+                         "note": "the march is round-latency bound (one barrier-separated round per 0.3 dnx/vmax of "
                                  "travel time), not bandwidth bound; see DESIGN.md"},
             "e2e": {"value": e2e_value, "unit": "node-solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "ALI_FMM.find_all_TTF_rays_parallel", "steps": e2e_steps, "s_per_step": e2e_s / e2e_steps},

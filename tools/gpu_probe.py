@@ -5,6 +5,9 @@ import time
 import os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
+from ali_fmm_and_ray_tracing_b200 import build as _b
+if os.environ.get("ALIFMM_LIB"):
+    _b.LIB_PATH = os.path.abspath(os.environ["ALIFMM_LIB"])
 from ali_fmm_and_ray_tracing_b200 import _capi
 from tests import models
 
