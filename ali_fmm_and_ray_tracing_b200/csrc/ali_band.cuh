@@ -131,13 +131,20 @@ ALI_DEV void ali_band_mark_dirty(const AliBandGrid &g, int iz, int ix)
 }
 
 // Phase B: make the staged value visible if it changed anything.
+ALI_DEV bool ali_band_changed(const AliBandGrid &g, int iz, int ix, double v)
+{
+    return !(g.T[(size_t)iz * g.nx + ix] == v);   // also true for a node without an estimate yet (NaN)
+}
+
+ALI_DEV void ali_band_store(const AliBandGrid &g, int iz, int ix, double v)
+{
+    g.T[(size_t)iz * g.nx + ix] = v;
+    ali_band_mark_dirty(g, iz, ix);
+}
+
 ALI_DEV void ali_band_publish(const AliBandGrid &g, int iz, int ix, double v)
 {
-    const size_t node = (size_t)iz * g.nx + ix;
-    if (!(g.T[node] == v)) {   // also true for a node without an estimate yet (NaN)
-        g.T[node] = v;
-        ali_band_mark_dirty(g, iz, ix);
-    }
+    if (ali_band_changed(g, iz, ix, v)) ali_band_store(g, iz, ix, v);
 }
 
 // Claims a far node for the band list; returns true for exactly one caller.
@@ -162,10 +169,27 @@ ALI_DEV int ali_band_accept(const AliBandGrid &g, int iz, int ix, unsigned *nb)
     const size_t node = (size_t)iz * g.nx + ix;
     int cnt = 0;
     g.st[node] = ALI_ST_ALIVE;
+#if defined(__CUDA_ARCH__)
+    // the four state words are loaded together (one memory latency), then only far ones are claimed
+    const bool hw = ix > 0, he = ix < g.nx - 1, hn = iz > 0, hs = iz < g.nz - 1;
+    const volatile unsigned long long *tw = (const volatile unsigned long long *)(g.T + node);
+    const unsigned long long vw = hw ? tw[-1] : 0ull, ve = he ? tw[1] : 0ull;
+    const unsigned long long vn = hn ? tw[-(long long)g.nx] : 0ull, vs = hs ? tw[g.nx] : 0ull;
+    unsigned long long *cw = (unsigned long long *)(g.T + node);
+    if (vw == ALI_T_FAR_BITS && atomicCAS(cw - 1, ALI_T_FAR_BITS, ALI_T_ENLISTED_BITS) == ALI_T_FAR_BITS)
+        nb[cnt++] = ALI_PACK(iz, ix - 1);
+    if (ve == ALI_T_FAR_BITS && atomicCAS(cw + 1, ALI_T_FAR_BITS, ALI_T_ENLISTED_BITS) == ALI_T_FAR_BITS)
+        nb[cnt++] = ALI_PACK(iz, ix + 1);
+    if (vn == ALI_T_FAR_BITS && atomicCAS(cw - g.nx, ALI_T_FAR_BITS, ALI_T_ENLISTED_BITS) == ALI_T_FAR_BITS)
+        nb[cnt++] = ALI_PACK(iz - 1, ix);
+    if (vs == ALI_T_FAR_BITS && atomicCAS(cw + g.nx, ALI_T_FAR_BITS, ALI_T_ENLISTED_BITS) == ALI_T_FAR_BITS)
+        nb[cnt++] = ALI_PACK(iz + 1, ix);
+#else
     if (ix > 0 && ali_band_claim(g, node - 1)) nb[cnt++] = ALI_PACK(iz, ix - 1);
     if (ix < g.nx - 1 && ali_band_claim(g, node + 1)) nb[cnt++] = ALI_PACK(iz, ix + 1);
     if (iz > 0 && ali_band_claim(g, node - g.nx)) nb[cnt++] = ALI_PACK(iz - 1, ix);
     if (iz < g.nz - 1 && ali_band_claim(g, node + g.nx)) nb[cnt++] = ALI_PACK(iz + 1, ix);
+#endif
     return cnt;
 }
 

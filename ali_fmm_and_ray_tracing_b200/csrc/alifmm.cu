@@ -63,7 +63,6 @@ struct AliBatch {
     double delta;
     double *T;              // [n_src][nz*nx]
     uint8_t *st;            // [n_src][nz*nx]
-    uint8_t *dirty;         // [n_src][nz*nx]
     // sequential scratch, per source
     double *seq_t;          // [n_src][2*seq_cap]
     int32_t *seq_s;         // [n_src][2*seq_cap]
@@ -190,6 +189,43 @@ __device__ __forceinline__ int ali_sort_bin(unsigned e, int isz, int isx)
     return k < 0 ? 0 : (k >= ALI_SORT_BINS ? ALI_SORT_BINS - 1 : k);
 }
 
+// "Window changed" marks of one round live in shared memory as a bitmap over the grid folded
+// modulo 512 x 512 nodes (32 KB).  A node that publishes a new value sets the bits of its 12
+// window neighbours; phase C tests one bit per surviving band node.  Two nodes 512 apart share
+// a bit: such a false mark only costs a re-evaluation, which returns the same value (the update
+// is a pure function of the window).  This replaces 12 scattered global byte stores per
+// published node and a global load + store per band node per round.
+#define ALI_DMAP_BITS 9
+#define ALI_DMAP_WORDS ((1 << (2 * ALI_DMAP_BITS)) / 32)
+__device__ __forceinline__ void ali_dmap_row(unsigned *dmap, int z, int x0, unsigned pattern)
+{
+    const unsigned m = (1u << ALI_DMAP_BITS) - 1u;
+    const unsigned row = ((unsigned)z & m) << (ALI_DMAP_BITS - 5);
+    const unsigned xs = (unsigned)x0 & m;
+    const unsigned long long bits = (unsigned long long)pattern << (xs & 31u);
+    const unsigned w0 = xs >> 5;
+    atomicOr(&dmap[row | w0], (unsigned)bits);
+    const unsigned hi = (unsigned)(bits >> 32);
+    if (hi) atomicOr(&dmap[row | ((w0 + 1u) & ((1u << (ALI_DMAP_BITS - 5)) - 1u))], hi);
+}
+
+// Sets the bits of the 12 window neighbours of (iz, ix) (slot layout of ali_core.cuh).
+__device__ __forceinline__ void ali_dmap_mark(unsigned *dmap, int iz, int ix)
+{
+    ali_dmap_row(dmap, iz - 2, ix - 2, 0x04u);
+    ali_dmap_row(dmap, iz - 1, ix - 2, 0x0eu);
+    ali_dmap_row(dmap, iz, ix - 2, 0x1bu);
+    ali_dmap_row(dmap, iz + 1, ix - 2, 0x0eu);
+    ali_dmap_row(dmap, iz + 2, ix - 2, 0x04u);
+}
+
+__device__ __forceinline__ bool ali_dmap_test(const unsigned *dmap, int iz, int ix)
+{
+    const unsigned m = (1u << ALI_DMAP_BITS) - 1u;
+    const unsigned xs = (unsigned)ix & m;
+    return (dmap[(((unsigned)iz & m) << (ALI_DMAP_BITS - 5)) | (xs >> 5)] >> (xs & 31u)) & 1u;
+}
+
 template <int NT>
 __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
 {
@@ -205,6 +241,8 @@ __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
     __shared__ AliBandGrid s_grid;   // copy for the out-of-line FD fallback
     __shared__ int s_bins[ALI_SORT_BINS];
     __shared__ int s_wsum[32];
+    __shared__ __align__(16) unsigned s_dmap[ALI_DMAP_WORDS];
+    __shared__ int s_force[2];   // by round parity: re-evaluate the whole band (FD fallback outside the register path)
     long long cyc[4] = {0, 0, 0, 0};
     const int isz = (b.sg > 1 ? b.sg : 1) * rec.src_iz, isx = (b.sg > 1 ? b.sg : 1) * rec.src_ix;
 
@@ -212,8 +250,8 @@ __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
     g.nz = b.nz; g.nx = b.nx;
     g.T = b.T + (size_t)src * b.nz * b.nx;
     g.st = b.st + (size_t)src * b.nz * b.nx;
-    g.dirty = b.dirty + (size_t)src * ali_dirty_bytes(b.nz, b.nx);
-    g.tiles_x = ali_dirty_tiles_x(b.nx);
+    g.dirty = nullptr;   // window-changed marks live in shared memory here (s_dmap); the byte map is the host replay's
+    g.tiles_x = 0;
     g.dnx = b.m.dnx;
     g.mv = ali_band_view(b.sg);
 
@@ -235,6 +273,7 @@ __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
         s_evalmin[0] = ~0ull; s_evalmin[1] = ~0ull; s_basemin[0] = ~0ull; s_basemin[1] = ~0ull;
         s_overflow = rec.overflow;
         s_evals = 0; s_fbs = 0;
+        s_force[0] = 0; s_force[1] = 0;
     }
     __syncthreads();
     if (s_overflow) return;
@@ -260,7 +299,7 @@ __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
             }
             int pos = ali_warp_reserve(k, &s_count[0]);
             if (k) {
-                if (pos < cap) { ent0[pos] = entry; wrk0[pos] = (unsigned)pos; }
+                if (pos < cap) { ent0[pos] = entry; wrk0[pos] = (unsigned)pos; val0[pos] = g.T[(size_t)ALI_PACK_Z(entry) * b.nx + ALI_PACK_X(entry)]; }
                 else s_overflow = 2;
             }
         }
@@ -282,39 +321,63 @@ __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
         rounds++;
         if (n > max_band) max_band = n;
         long long t0 = clock64();
-        // phase A: evaluate the work list from the round's snapshot
-        for (int q = tid; q < nwork; q += NT) {
+        // phase A: evaluate the work list from the round's snapshot.  The first two items of a thread
+        // stay in registers for phase B (a round rarely has more than 2 * NT items); the minimum of
+        // the new values is reduced here so that phase B has nothing to wait for.
+        if (tid == 0) { s_count[cur ^ 1] = 0; s_nwork[cur ^ 1] = 0; s_basemin[cur ^ 1] = ~0ull; s_evalmin[cur ^ 1] = ~0ull; }
+        for (int q = tid; q < ALI_DMAP_WORDS / 4; q += NT) reinterpret_cast<uint4 *>(s_dmap)[q] = make_uint4(0u, 0u, 0u, 0u);
+        double lmin = 1e300;
+        unsigned pe0 = 0, pe1 = 0;
+        double pv0 = 0.0, pv1 = 0.0;
+        int pmask = 0, it = 0;
+        for (int q = tid; q < nwork; q += NT, it++) {
             const int i = (int)wrk[q];
             const unsigned e = ent[i];
             const int iz = ALI_PACK_Z(e), ix = ALI_PACK_X(e);
             int fb = 0;
-            const size_t di = ali_dirty_index(g, iz, ix);
-            g.dirty[di] = 0;
-            val[i] = ali_band_eval(b.m, b.m_dev, g, &s_grid, iz, ix, &fb);
-            if (fb) g.dirty[di] = 1; // the fallback also reads alive flags: always re-evaluate
+            const double vold = val[i];   // the value this node last published (0: none yet)
+            const double v = ali_band_eval(b.m, b.m_dev, g, &s_grid, iz, ix, &fb);
+            val[i] = v;
             my_evals++;
             my_fbs += fb;
-        }
-        __syncthreads();
-        long long t1 = clock64();
-        // phase B: publish the re-evaluated values; tmin over the whole band
-        if (tid == 0) { s_count[cur ^ 1] = 0; s_nwork[cur ^ 1] = 0; s_basemin[cur ^ 1] = ~0ull; s_evalmin[cur ^ 1] = ~0ull; }
-        double lmin = 1e300;
-        for (int q = tid; q < nwork; q += NT) {
-            const int i = (int)wrk[q];
-            const unsigned e = ent[i];
-            const double v = val[i];
-            ali_band_publish(g, ALI_PACK_Z(e), ALI_PACK_X(e), v);
             lmin = fmin(lmin, v);
+            if (it == 0) { pe0 = e; pv0 = v; pmask |= (v != vold ? 1 : 0) | (fb ? 4 : 0); }
+            else if (it == 1) { pe1 = e; pv1 = v; pmask |= (v != vold ? 2 : 0) | (fb ? 8 : 0); }
+            else {
+                // rare: more than 2 * NT items in one round; published from memory in phase B
+                if (v != vold) val[i] = -v;          // sign marks "changed" until phase B
+                if (fb) s_force[rounds & 1] = 1;
+            }
         }
         for (int o = 16; o > 0; o >>= 1) lmin = fmin(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
         if ((tid & 31) == 0 && lmin < 1e300)
             atomicMin(&s_evalmin[cur], (unsigned long long)__double_as_longlong(lmin));
         __syncthreads();
+        long long t1 = clock64();
+        // phase B: publish the re-evaluated values that changed and mark their window neighbours.
+        // A node the FD fallback evaluated also depends on alive flags: it is re-evaluated every
+        // round (its own bit), like the reference re-evaluates it on every neighbouring pop.
+        if (tid == 0) s_force[(rounds + 1) & 1] = 0;
+        if (pmask & 1) { g.T[(size_t)ALI_PACK_Z(pe0) * g.nx + ALI_PACK_X(pe0)] = pv0; ali_dmap_mark(s_dmap, ALI_PACK_Z(pe0), ALI_PACK_X(pe0)); }
+        if (pmask & 2) { g.T[(size_t)ALI_PACK_Z(pe1) * g.nx + ALI_PACK_X(pe1)] = pv1; ali_dmap_mark(s_dmap, ALI_PACK_Z(pe1), ALI_PACK_X(pe1)); }
+        if (pmask & 4) ali_dmap_row(s_dmap, ALI_PACK_Z(pe0), ALI_PACK_X(pe0), 1u);
+        if (pmask & 8) ali_dmap_row(s_dmap, ALI_PACK_Z(pe1), ALI_PACK_X(pe1), 1u);
+        for (int q = tid + 2 * NT; q < nwork; q += NT) {
+            const int i = (int)wrk[q];
+            const unsigned e = ent[i];
+            const double v = val[i];
+            if (v < 0.0) {
+                val[i] = -v;
+                g.T[(size_t)ALI_PACK_Z(e) * g.nx + ALI_PACK_X(e)] = -v;
+                ali_dmap_mark(s_dmap, ALI_PACK_Z(e), ALI_PACK_X(e));
+            }
+        }
+        __syncthreads();
         long long t2 = clock64();
         // phase C: accept + extend the band; compact survivors; next work list (deferred to the
         // re-sort pass on the rounds that re-order the list along the front)
         const bool resort = b.resort_every > 0 && (rounds % b.resort_every) == 0;
+        const int force = s_force[rounds & 1];
         const unsigned long long tminb = s_evalmin[cur] < s_basemin[cur] ? s_evalmin[cur] : s_basemin[cur];
         const double thr = __longlong_as_double((long long)tminb) + b.delta;
         double bmin = 1e300;
@@ -334,8 +397,7 @@ __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
                 } else {
                     out[0] = e; k = 1;
                     if (!resort) {
-                        const size_t di = ali_dirty_index(g, iz, ix);
-                        if (g.dirty[di]) { g.dirty[di] = 0; kw = 1; }
+                        if (force || ali_dmap_test(s_dmap, iz, ix)) kw = 1;
                         else bmin = fmin(bmin, v);
                     }
                 }
@@ -422,8 +484,7 @@ __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
                     const double v = val[i];
                     if (v == 0.0) kw = 1;           // new node: no estimate yet
                     else {
-                        const size_t di = ali_dirty_index(g, ALI_PACK_Z(e), ALI_PACK_X(e));
-                        if (g.dirty[di]) { g.dirty[di] = 0; kw = 1; }
+                        if (force || ali_dmap_test(s_dmap, ALI_PACK_Z(e), ALI_PACK_X(e))) kw = 1;
                         else bm = fmin(bm, v);
                     }
                 }
@@ -653,7 +714,7 @@ struct alifmm_ctx {
     int band_smem_bytes = 0;   // measured on B200: L1 for the T / status gathers is worth more than smem lists
     // resident batch
     int n_slots = 0, sg = 0, fz = 0, fx = 0;
-    DevBuf T, st, dirty, seq_t, seq_s, seq_heap, lists, stage, rec, jobs, ray_x, ray_y, ray_time, ray_len, ray_flag, misc;
+    DevBuf T, st, seq_t, seq_s, seq_heap, lists, stage, rec, jobs, ray_x, ray_y, ray_time, ray_len, ray_flag, misc;
     alifmm_counters_t cnt{};
 };
 
@@ -700,7 +761,7 @@ extern "C" void alifmm_destroy(alifmm_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (void *p : c->model_allocs) cudaFree(p);
-    DevBuf *bufs[] = {&c->T, &c->st, &c->dirty, &c->seq_t, &c->seq_s, &c->seq_heap, &c->lists, &c->stage, &c->rec, &c->jobs,
+    DevBuf *bufs[] = {&c->T, &c->st, &c->seq_t, &c->seq_s, &c->seq_heap, &c->lists, &c->stage, &c->rec, &c->jobs,
                       &c->ray_x, &c->ray_y, &c->ray_time, &c->ray_len, &c->ray_flag, &c->misc};
     for (DevBuf *b : bufs) dev_release(*b);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
@@ -882,15 +943,13 @@ static int ttf_attempt(alifmm_ctx *c, int32_t n_src, const int32_t *src_iz, cons
     int rc;
     if ((rc = dev_reserve(c->T, (size_t)n_src * N * sizeof(double))) != 0) return rc;
     if ((rc = dev_reserve(c->st, (size_t)n_src * N + 16)) != 0) return rc;
-    const size_t dirty_bytes = ali_dirty_bytes(fz, fx);
-    if ((rc = dev_reserve(c->dirty, (size_t)n_src * dirty_bytes + 16)) != 0) return rc;
     if ((rc = dev_reserve(c->seq_t, (size_t)n_src * 2 * b.seq_cap * sizeof(double))) != 0) return rc;
     if ((rc = dev_reserve(c->seq_s, (size_t)n_src * 2 * b.seq_cap * sizeof(int32_t))) != 0) return rc;
     if ((rc = dev_reserve(c->seq_heap, (size_t)n_src * 2 * b.heap_cap * sizeof(int32_t))) != 0) return rc;
     if ((rc = dev_reserve(c->lists, (size_t)n_src * 4 * b.band_cap * sizeof(unsigned))) != 0) return rc;
     if ((rc = dev_reserve(c->stage, (size_t)n_src * 2 * b.band_cap * sizeof(double))) != 0) return rc;
     if ((rc = dev_reserve(c->rec, (size_t)n_src * sizeof(AliSourceRec))) != 0) return rc;
-    b.T = (double *)c->T.p; b.st = (uint8_t *)c->st.p; b.dirty = (uint8_t *)c->dirty.p;
+    b.T = (double *)c->T.p; b.st = (uint8_t *)c->st.p;
     b.seq_t = (double *)c->seq_t.p; b.seq_s = (int32_t *)c->seq_s.p; b.seq_heap = (int32_t *)c->seq_heap.p;
     b.lists = (unsigned *)c->lists.p; b.stage = (double *)c->stage.p; b.rec = (AliSourceRec *)c->rec.p;
 
@@ -903,7 +962,6 @@ static int ttf_attempt(alifmm_ctx *c, int32_t n_src, const int32_t *src_iz, cons
     CUDA_TRY(cudaEventRecord(c->ev[0], s));
     CUDA_TRY(cudaMemsetAsync(b.T, ALI_T_UNSET_BYTE, (size_t)n_src * N * sizeof(double), s)); // NaN = no estimate
     CUDA_TRY(cudaMemsetAsync(b.st, 0, (size_t)n_src * N, s));
-    CUDA_TRY(cudaMemsetAsync(b.dirty, 0, (size_t)n_src * dirty_bytes, s));
     ali_seq_kernel<<<n_src, 32, 0, s>>>(b);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(c->ev[1], s));
