@@ -27,6 +27,8 @@ struct AliSeqGrid {
     int32_t *st;
     int wz0, wx0, wnz, wnx;
     int32_t *heap;        // (iz, ix) pairs, 1-indexed (ATR:118-119)
+    double *cv;           // evaluation cache, window-indexed like st (cooperative march only)
+    uint8_t *cf;          // 1: cv holds the update of this node for the current state of its window
     int ntr, heap_cap;
     int overflow;
     AliMatView mv;
@@ -36,6 +38,7 @@ struct AliSeqGrid {
     {
         return z >= wz0 && z < wz0 + wnz && x >= wx0 && x < wx0 + wnx;
     }
+    ALI_DEV size_t widx(int z, int x) const { return (size_t)(z - wz0) * wnx + (x - wx0); }
     ALI_DEV int32_t &s(int z, int x) const { return st[(size_t)(z - wz0) * wnx + (x - wx0)]; }
     ALI_DEV int32_t status(int z, int x) const { return in_win(z, x) ? s(z, x) : -1; }
     ALI_DEV bool avail(int z, int x) const { return in_win(z, x) && s(z, x) >= 0; }
@@ -130,6 +133,7 @@ ALI_DEV void ali_downtree(AliSeqGrid &g)
 struct AliSeqCounters {
     long long pops, evals, fallbacks;
     long long cyc_heap, cyc_eval;   // device builds: SM cycles in heap operations / evaluations
+    long long steps, computed;      // cooperative march: warp-wide evaluation steps, evaluations executed in them
 };
 
 #if defined(__CUDA_ARCH__)
@@ -204,11 +208,184 @@ ALI_DEV int ali_seq_march(AliSeqGrid &g, const AliModel &m, int cx, int cz, int 
     return why;
 }
 
+// ---------------------------------------------------------------------------
+// Cooperative form of the same march: identical result, shorter critical path.
+//
+// The heap order is inherently sequential, but the expensive part of a pop -- the ALI update
+// of the popped node's neighbours -- is a pure function of the neighbour's 12-node window
+// (values + availability), its material and the grid edges.  So its result can be computed
+// ahead of time and kept until a node of that window changes:
+//   * cv/cf cache the update of a node for the current state of its window.  Whenever a node
+//     receives a new value (or its first one) the flags of its 12 window neighbours are
+//     cleared.  A re-evaluation the reference performs on an unchanged window (97 % of its
+//     re-evaluations on the weld) is answered from the cache.
+//   * Lane 0 walks the reference's loop.  When it needs an update that is not cached it stops,
+//     and the whole warp evaluates in one step: lane 0 the missing node, the other lanes the
+//     not-yet-cached neighbours of the nodes in the first heap positions (the next pops).
+// Results of the FD fallback are never cached (it also reads alive flags), nor are the
+// evaluations level 1 of travel() makes with the wrong nnz (ATR:1645).
+// ---------------------------------------------------------------------------
+struct AliCoopState {
+    int have_p, iz, ix, s;       // popped node whose neighbours are being visited, next neighbour
+    int miss, mz, mx, mnnz;      // evaluation lane 0 is waiting for
+    int miss_ready, miss_fb;
+    double miss_v;
+    int finished, why;
+};
+
+ALI_DEV void ali_seq_invalidate(const AliSeqGrid &g, int z, int x)
+{
+    if (z - 2 >= g.wz0 && z + 2 < g.wz0 + g.wnz && x - 2 >= g.wx0 && x + 2 < g.wx0 + g.wnx) {
+        uint8_t *f = g.cf + g.widx(z, x);
+        const int w = g.wnx;
+        f[-2 * w] = 0; f[-w - 1] = 0; f[-w] = 0; f[-w + 1] = 0;
+        f[-2] = 0; f[-1] = 0; f[1] = 0; f[2] = 0;
+        f[w - 1] = 0; f[w] = 0; f[w + 1] = 0; f[2 * w] = 0;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 12; k++) {
+            const int zz = z + ALI_W_DZ(k), xx = x + ALI_W_DX(k);
+            if (g.in_win(zz, xx)) g.cf[g.widx(zz, xx)] = 0;
+        }
+    }
+}
+
+#define ALI_COOP_HEAP_POSITIONS 8
+// One lane's share of an evaluation step.  ntr: current heap size (lane 0's value).
+ALI_DEV int ali_coop_step(const AliSeqGrid &g, const AliModel &m, AliCoopState &cs, int lane, int ntr)
+{
+    const int nnx = g.nx, nnz = g.nz;
+    int cz = 0, cx = 0, cnnz = nnz;
+    bool want = false;
+    const bool serve = (lane == 0 && cs.miss);
+    if (serve) {
+        cz = cs.mz; cx = cs.mx; cnnz = cs.mnnz;
+        want = true;
+    } else {
+        const int slot = lane == 0 ? 4 * ALI_COOP_HEAP_POSITIONS - 1 : lane - 1;
+        const int hp = 1 + (slot >> 2), dir = slot & 3;
+        if (hp <= ntr && hp <= ALI_COOP_HEAP_POSITIONS) {
+            cz = g.heap[2 * hp]; cx = g.heap[2 * hp + 1];
+            if (dir == 0) cx -= 1; else if (dir == 1) cx += 1; else if (dir == 2) cz -= 1; else cz += 1;
+            if (cz >= 0 && cz < nnz && cx >= 0 && cx < nnx && g.in_win(cz, cx))
+                want = g.s(cz, cx) != 0 && g.cf[g.widx(cz, cx)] == 0;
+        }
+    }
+    if (want) {
+        int fb = 0;
+        const double v = ali_eval_node(m, g.mv, g, cz, cx, cnnz, nnx, nnz, nnx, g.dnx, &fb);
+        if (serve) {
+            cs.miss_v = v; cs.miss_fb = fb; cs.miss_ready = 1; cs.miss = 0;
+        } else if (!fb) {
+            g.cv[g.widx(cz, cx)] = v;
+            g.cf[g.widx(cz, cx)] = 1;
+        }
+    }
+    return want ? 1 : 0;
+}
+
+// Lane 0: the reference's loop (same order of heap operations as ali_seq_march) until it ends
+// (returns 1) or needs an update that is not cached (returns 0 with cs.miss set).
+ALI_DEV int ali_coop_advance(AliSeqGrid &g, AliCoopState &cs, int cx, int cz, int max_dist, int nnz_bug, int stop_r,
+                             AliSeqCounters &cnt)
+{
+    const int nnx = g.nx, nnz = g.nz;
+    for (;;) {
+        if (!cs.have_p) {
+            if (g.ntr <= 0 || cs.finished) return 1;
+            cs.ix = g.heap[3]; cs.iz = g.heap[2];
+            g.s(cs.iz, cs.ix) = 0;
+            ali_downtree(g);
+            cnt.pops++;
+            cs.s = 0;
+            cs.have_p = 1;
+        }
+        const int iz = cs.iz, ix = cs.ix;
+        for (; cs.s < 4; cs.s++) {
+            const int s = cs.s;
+            int z = iz, x = ix;
+            if (s == 0) x = ix - 1; else if (s == 1) x = ix + 1; else if (s == 2) z = iz - 1; else z = iz + 1;
+            const bool inside = (s < 2) ? (0 <= x && x <= nnx - 1) : (0 <= z && z <= nnz - 1);
+            if (inside) {
+                if (!g.in_win(z, x)) { cs.finished = 1; cs.why = ALI_SEQ_LIMIT; continue; }
+                const int32_t stv = g.s(z, x);
+                if (stv != 0) {
+                    const int nnz_l = (nnz_bug && s < 2 && stv > 0) ? nnx : nnz;
+                    const size_t wi = g.widx(z, x);
+                    double v;
+                    int fb = 0;
+                    if (cs.miss_ready) { v = cs.miss_v; fb = cs.miss_fb; cs.miss_ready = 0; }
+                    else if (nnz_l == nnz && g.cf[wi]) v = g.cv[wi];
+                    else { cs.miss = 1; cs.mz = z; cs.mx = x; cs.mnnz = nnz_l; return 0; }
+                    cnt.evals++;
+                    cnt.fallbacks += fb;
+                    const bool changed = (stv == -1) || !(g.tt(z, x) == v);
+                    g.tref(z, x) = v;
+                    if (changed) ali_seq_invalidate(g, z, x);
+                    if (nnz_l == nnz && !fb) { g.cv[wi] = v; g.cf[wi] = 1; }
+                    else g.cf[wi] = 0;
+                    if (stv == -1) ali_addtree(g, z, x);
+                    else ali_updtree(g, z, x);
+                }
+            } else if (max_dist >= 0) {
+                int d = (s < 2) ? (cx - x) : (cz - z);
+                if (d < 0) d = -d;
+                if (d == max_dist + 1) { cs.finished = 1; cs.why = ALI_SEQ_BOX; }
+            }
+        }
+        cs.have_p = 0;
+        if (stop_r >= 0 && cs.why != ALI_SEQ_BOX) {
+            int dz = iz - cz, dx = ix - cx;
+            if (dz < 0) dz = -dz;
+            if (dx < 0) dx = -dx;
+            if ((dz > dx ? dz : dx) >= stop_r) { cs.finished = 1; if (cs.why == ALI_SEQ_EMPTY) cs.why = ALI_SEQ_HANDOVER; }
+        }
+        if (g.overflow) { cs.finished = 1; cs.why = ALI_SEQ_LIMIT; }
+    }
+}
+
+// Same contract as ali_seq_march; every lane of the warp calls it (the host replay passes
+// nlanes and plays the lanes one after the other).  Only lane 0's g / cnt are meaningful.
+ALI_DEV int ali_seq_march_coop(AliSeqGrid &g, const AliModel &m, int cx, int cz, int max_dist, int nnz_bug,
+                               int stop_r, AliSeqCounters &cnt, int lane, int nlanes)
+{
+    AliCoopState cs;
+    cs.have_p = 0; cs.iz = cs.ix = cs.s = 0;
+    cs.miss = 0; cs.mz = cs.mx = cs.mnnz = 0;
+    cs.miss_ready = 0; cs.miss_fb = 0; cs.miss_v = 0.0;
+    cs.finished = 0; cs.why = ALI_SEQ_EMPTY;
+    for (;;) {
+        int done = 0;
+#if defined(__CUDA_ARCH__)
+        const int ntr = __shfl_sync(0xffffffffu, g.ntr, 0);
+        const int did = ali_coop_step(g, m, cs, lane, ntr);
+        const unsigned mask = __ballot_sync(0xffffffffu, did);
+        if (lane == 0) {
+            cnt.steps++;
+            cnt.computed += __popc(mask);
+            done = ali_coop_advance(g, cs, cx, cz, max_dist, nnz_bug, stop_r, cnt);
+        }
+        __syncwarp();
+        done = __shfl_sync(0xffffffffu, done, 0);
+#else
+        (void)lane;
+        cnt.steps++;
+        for (int l = 0; l < nlanes; l++) cnt.computed += ali_coop_step(g, m, cs, l, g.ntr);
+        done = ali_coop_advance(g, cs, cx, cz, max_dist, nnz_bug, stop_r, cnt);
+#endif
+        if (done) break;
+    }
+    if (!cs.finished) cs.why = ALI_SEQ_EMPTY;
+    return cs.why;
+}
+
 // Resets a level grid: T = 0, status = far.  Cooperative over `nlanes` lanes.
 ALI_DEV void ali_seq_clear(AliSeqGrid &g, bool clear_t, int lane, int nlanes)
 {
     size_t n = (size_t)g.wnz * g.wnx;
     for (size_t i = lane; i < n; i += nlanes) g.st[i] = -1;
+    if (g.cf)
+        for (size_t i = lane; i < n; i += nlanes) g.cf[i] = 0;
     if (clear_t)
         for (size_t i = lane; i < n; i += nlanes) g.t[i] = 0.0; // level grids only (window == grid)
     g.ntr = 0;
@@ -333,6 +510,8 @@ struct AliSeqScratch {
     double *tA, *tB;     // level T buffers (ping-pong), each max_level_nodes
     int32_t *sA, *sB;    // level status buffers; sB is re-used for the main-grid window
     int32_t *heap;       // 2 * heap_cap
+    double *cval;        // evaluation cache of the grid being marched (status_cap entries), or nullptr
+    uint8_t *cflag;
     int heap_cap;
     size_t status_cap;   // entries available in sA / sB
 };
@@ -367,6 +546,7 @@ ALI_DEV void ali_src_begin(AliSrcState &s, const AliSourcePlan &p)
     s.cz[0] = s.cz[1] = s.cx[0] = s.cx[1] = 0;
     s.cnt.pops = s.cnt.evals = s.cnt.fallbacks = 0;
     s.cnt.cyc_heap = s.cnt.cyc_eval = 0;
+    s.cnt.steps = s.cnt.computed = 0;
     s.overflow = 0;
     s.base = ali_make_view(1, 0, 0, p.fine ? p.sg : 1, p.fine ? 1 : 0);
 }
@@ -386,6 +566,7 @@ ALI_DEV void ali_src_level_geometry(AliSrcState &s, const AliModel &m, const Ali
     g.t_stride = g.nx;
     g.wz0 = 0; g.wx0 = 0; g.wnz = g.nz; g.wnx = g.nx;
     g.heap = sc.heap; g.heap_cap = sc.heap_cap;
+    g.cv = sc.cval; g.cf = sc.cflag;
     g.mv = ali_make_view(scl, bottom, left, p.fine ? p.sg : 1, 1);
     g.dnx = m.dnx / scl;
     s.cx[cur] = scl * (p.isx - left);
@@ -429,6 +610,15 @@ ALI_DEV int ali_src_level_seq(AliSrcState &s, const AliModel &m, const AliSource
     return why;
 }
 
+ALI_DEV int ali_src_level_seq_coop(AliSrcState &s, const AliModel &m, const AliSourcePlan &p, int l, int lane, int nlanes)
+{
+    const int cur = l & 1;
+    int why = ali_seq_march_coop(s.lv[cur], m, s.cx[cur], s.cz[cur], p.scale[l] * p.size[l],
+                                 (!p.fine && l == 0) ? 1 : 0, -1, s.cnt, lane, nlanes);
+    s.overflow |= s.lv[cur].overflow;
+    return why;
+}
+
 ALI_DEV void ali_src_main_geometry(AliSrcState &s, const AliModel &m, const AliSourcePlan &p, const AliSeqScratch &sc,
                                    double *T)
 {
@@ -442,6 +632,7 @@ ALI_DEV void ali_src_main_geometry(AliSrcState &s, const AliModel &m, const AliS
     mg.wnz = ali_imin(p.nz - 1, p.isz + half) - mg.wz0 + 1;
     mg.wnx = ali_imin(p.nx - 1, p.isx + half) - mg.wx0 + 1;
     mg.heap = sc.heap; mg.heap_cap = sc.heap_cap;
+    mg.cv = sc.cval; mg.cf = sc.cflag;
     mg.mv = s.base;
     mg.dnx = m.dnx;
     if ((size_t)mg.wnz * mg.wnx > sc.status_cap) s.overflow = 1;
@@ -455,28 +646,38 @@ ALI_DEV void ali_src_main_start_and_seq(AliSrcState &s, const AliModel &m, const
     s.overflow |= s.mg.overflow;
 }
 
-// All-sequential form: levels + main-grid start for one source.  `T` is the source's main-grid
-// field.  Lanes other than 0 only take part in the fills.
+// Levels + main-grid start for one source.  `T` is the source's main-grid field.  With an
+// evaluation cache in the scratch (sc.cval) the marches run in their cooperative form, else lane
+// 0 alone walks them and the other lanes only take part in the fills.
 ALI_DEV void ali_seq_source(const AliModel &m, const AliSourcePlan &p, const AliSeqScratch &sc, double *T,
                             AliSeqResult &res, int lane, int nlanes)
 {
     AliSrcState s;
+    const bool coop = sc.cval != nullptr;
     ali_src_begin(s, p);
     for (int l = 0; l < p.nlev; l++) {
         ali_src_level_geometry(s, m, p, sc, l);
         ali_src_level_fill(s, m, p, l, lane, nlanes, true);
         ALI_SYNCWARP();
-        if (lane == 0) {
-            ali_src_level_start(s, p, l);
-            ali_src_level_seq(s, m, p, l, -1);
-        }
+        if (lane == 0) ali_src_level_start(s, p, l);
+        ALI_SYNCWARP();
+        if (coop) ali_src_level_seq_coop(s, m, p, l, lane, nlanes);
+        else if (lane == 0) ali_src_level_seq(s, m, p, l, -1);
         ALI_SYNCWARP();
     }
     ali_src_main_geometry(s, m, p, sc, T);
+#if defined(__CUDA_ARCH__)
+    s.overflow = __shfl_sync(0xffffffffu, s.overflow, 0);
+#endif
     if (!s.overflow) {
         ali_seq_clear(s.mg, false, lane, nlanes);
         ALI_SYNCWARP();
-        if (lane == 0) ali_src_main_start_and_seq(s, m, p);
+        const int last = (p.nlev - 1) & 1;
+        if (lane == 0) ali_seq_handoff(s.lv[last], s.cz[last], s.cx[last], s.mg, p.isz, p.isx);
+        ALI_SYNCWARP();
+        if (coop) ali_seq_march_coop(s.mg, m, p.isx, p.isz, -1, 0, p.stop_r, s.cnt, lane, nlanes);
+        else if (lane == 0) ali_seq_march(s.mg, m, p.isx, p.isz, -1, 0, p.stop_r, s.cnt);
+        s.overflow |= s.mg.overflow;
         ALI_SYNCWARP();
     }
     res.wz0 = s.mg.wz0; res.wx0 = s.mg.wx0; res.wnz = s.mg.wnz; res.wnx = s.mg.wnx;

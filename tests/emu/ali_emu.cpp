@@ -191,7 +191,11 @@ static void band_to_seq(const AliBandGrid &bg, AliSeqGrid &g)
 
 // counters: [0] seq pops, [1] seq evals, [2] seq fallbacks, [3] band rounds, [4] band evals,
 //           [5] band fallbacks, [6] max list length, [7] overflow flag, [8] level band rounds,
-//           [9] level band evals
+//           [9] level band evals, [10] cooperative steps, [11] evaluations executed in them
+// Lanes of the cooperative sequential march (ali_seq.cuh); 0 = lane 0 alone walks the reference's loop.
+static int g_coop_lanes = 32;
+extern "C" void emu_set_coop(int nlanes) { g_coop_lanes = nlanes; }
+
 extern "C" int emu_ttf(int nz, int nx, const double *veln, const int32_t *velpn, const double *vel_map,
                        const long long *stif, int has_stif, const double *group_tab, const double *phase_tab,
                        int ncol, double dnx, int src_iz, int src_ix, int sg, int margin, double delta_frac,
@@ -211,6 +215,11 @@ extern "C" int emu_ttf(int nz, int nx, const double *veln, const int32_t *velpn,
     AliSeqScratch sc;
     sc.tA = tA.data(); sc.tB = tB.data(); sc.sA = sA.data(); sc.sB = sB.data();
     sc.heap = heap.data(); sc.heap_cap = (int)(cap / 2 + 64); sc.status_cap = cap;
+    std::vector<double> cval(g_coop_lanes > 0 ? cap : 0);
+    std::vector<uint8_t> cflag(g_coop_lanes > 0 ? cap : 0);
+    sc.cval = g_coop_lanes > 0 ? cval.data() : nullptr;
+    sc.cflag = g_coop_lanes > 0 ? cflag.data() : nullptr;
+    const bool coop = g_coop_lanes > 0 && level_margin < 0;
     std::memset(T, ALI_T_UNSET_BYTE, n * sizeof(double)); // NaN = no estimate
     const double delta = delta_frac * dnx / vmax;   // the levels scale it with their spacing
 
@@ -225,7 +234,7 @@ extern "C" int emu_ttf(int nz, int nx, const double *veln, const int32_t *velpn,
         AliSeqGrid &g = s.lv[l & 1];
         const int ring = ali_src_level_ring(p, l);
         const int stop_r = level_margin >= 0 ? ring + level_margin : -1;
-        int why = ali_src_level_seq(s, m, p, l, stop_r);
+        int why = coop ? ali_src_level_seq_coop(s, m, p, l, 0, g_coop_lanes) : ali_src_level_seq(s, m, p, l, stop_r);
         if (why == ALI_SEQ_HANDOVER) {
             // band rounds on the level grid until the front leaves the refined box
             AliBandGrid bg;
@@ -254,7 +263,15 @@ extern "C" int emu_ttf(int nz, int nx, const double *veln, const int32_t *velpn,
     counters[7] = s.overflow;
     if (s.overflow) return -1;
     ali_seq_clear(s.mg, false, 0, 1);
-    ali_src_main_start_and_seq(s, m, p);
+    if (coop) {
+        const int last = (p.nlev - 1) & 1;
+        ali_seq_handoff(s.lv[last], s.cz[last], s.cx[last], s.mg, p.isz, p.isx);
+        ali_seq_march_coop(s.mg, m, p.isx, p.isz, -1, 0, p.stop_r, s.cnt, 0, g_coop_lanes);
+        s.overflow |= s.mg.overflow;
+    } else {
+        ali_src_main_start_and_seq(s, m, p);
+    }
+    counters[10] = s.cnt.steps; counters[11] = s.cnt.computed;
     counters[0] = s.cnt.pops; counters[1] = s.cnt.evals; counters[2] = s.cnt.fallbacks;
     counters[7] = s.overflow;
     if (s.overflow) return -1;

@@ -36,6 +36,11 @@ def set_noise(p, seed=0):
     lib().emu_set_noise(ctypes.c_double(p), ctypes.c_ulonglong(seed))
 
 
+def set_coop(nlanes):
+    """Lanes of the cooperative sequential march the replay plays (kernel: 32); 0 = the plain sequential loop."""
+    lib().emu_set_coop(int(nlanes))
+
+
 def model_vmax(m, dnx):
     return lib().emu_model_vmax(*_margs(m, dnx))
 
@@ -47,12 +52,12 @@ def ttf(m, dnx, src_iz, src_ix, sg=1, margin=27, frac=0.3, vmax=None, eager=Fals
     nz = sg * (m.nz - 1) + 1 if sg > 1 else m.nz
     nx = sg * (m.nx - 1) + 1 if sg > 1 else m.nx
     T = np.zeros((nz, nx))
-    cnt = np.zeros(10, dtype=np.int64)
+    cnt = np.zeros(12, dtype=np.int64)
     rc = lib().emu_ttf(*_margs(m, dnx), int(src_iz), int(src_ix), int(sg), int(margin), ctypes.c_double(frac),
                        ctypes.c_double(vmax), int(eager), int(level_margin), _p(T, _f64p),
                        cnt.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)))
     names = ["seq_pops", "seq_evals", "seq_fallbacks", "rounds", "band_evals", "band_fallbacks", "max_list", "overflow",
-             "level_rounds", "level_evals"]
+             "level_rounds", "level_evals", "coop_steps", "coop_computed"]
     return T, dict(zip(names, cnt.tolist())), rc
 
 
