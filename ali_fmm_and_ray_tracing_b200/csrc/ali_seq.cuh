@@ -10,6 +10,7 @@
 // the source, where the band-synchronous kernel (ali_kernels.cu) takes over.
 #pragma once
 #include "ali_core.cuh"
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define ALI_SYNCWARP() __syncwarp()
@@ -20,13 +21,24 @@
 // Node state of one grid during the sequential march.  Status follows the reference:
 // -1 far, 0 alive, >0 position in the heap (ATR:103).  Status is stored for a window
 // [wz0, wz0+wnz) x [wx0, wx0+wnx) only; everything outside it is far by construction.
+// Heap entry: the node as (iz << 16) | ix plus its index in the status window, so that the status
+// updates of the heap operations need no address arithmetic.  One 8-byte word.
+struct alignas(8) AliHeapEnt {
+    unsigned zx, wi;
+};
+#define ALI_ENT_Z(e) ((int)((e).zx >> 16))
+#define ALI_ENT_X(e) ((int)((e).zx & 0xffffu))
+
 struct AliSeqGrid {
     int nz, nx;           // full extents of this grid (edge logic, absolute coordinates)
     double *t;            // T(z, x) = t[z * t_stride + x]
     long long t_stride;
     int32_t *st;
     int wz0, wx0, wnz, wnx;
-    int32_t *heap;        // (iz, ix) pairs, 1-indexed (ATR:118-119)
+    AliHeapEnt *heap;     // 1-indexed (ATR:118-119): packed node + its window index
+    double *hkey;         // hkey[pos] == T of the node at heap position pos: saves the dependent T load per comparison
+    int ndup;             // nodes with two heap entries (seed corners, ATR:1601-1612): both entries follow T
+    unsigned dup0, dup1, dup2, dup3;   // packed (iz << 16 | ix); scalars so that a by-value copy of the grid stays in registers
     double *cv;           // evaluation cache, window-indexed like st (cooperative march only)
     uint8_t *cf;          // 1: cv holds the update of this node for the current state of its window
     int ntr, heap_cap;
@@ -41,7 +53,14 @@ struct AliSeqGrid {
     ALI_DEV size_t widx(int z, int x) const { return (size_t)(z - wz0) * wnx + (x - wx0); }
     ALI_DEV int32_t &s(int z, int x) const { return st[(size_t)(z - wz0) * wnx + (x - wx0)]; }
     ALI_DEV int32_t status(int z, int x) const { return in_win(z, x) ? s(z, x) : -1; }
-    ALI_DEV bool avail(int z, int x) const { return in_win(z, x) && s(z, x) >= 0; }
+    // A node has an estimate (reference: nsts >= 0) exactly when its T is not NaN: level grids are
+    // reset to NaN, the main field is pre-filled with NaN, values are only ever written together with
+    // a status >= 0.  Outside the status window the main field is NaN.  The grid test stays: level 1 of
+    // travel() asks with a wrong nnz (ATR:1645) and would read past the level otherwise.
+    ALI_DEV bool avail(int z, int x) const
+    {
+        return z >= 0 && z < nz && x >= 0 && x < nx && t[(long long)z * t_stride + x] >= 0.0;
+    }
     ALI_DEV bool alive(int z, int x) const { return in_win(z, x) && s(z, x) == 0; }
     ALI_DEV double &tref(int z, int x) const { return t[(long long)z * t_stride + x]; }
     ALI_DEV double tt(int z, int x) const { return t[(long long)z * t_stride + x]; }
@@ -55,78 +74,125 @@ ALI_DEV int ali_half_round(int k)
     return h;
 }
 
-ALI_DEV void ali_heap_swap(AliSeqGrid &g, int a, int b)
-{
-    int32_t e0 = g.heap[2 * a], e1 = g.heap[2 * a + 1];
-    g.heap[2 * a] = g.heap[2 * b]; g.heap[2 * a + 1] = g.heap[2 * b + 1];
-    g.heap[2 * b] = e0; g.heap[2 * b + 1] = e1;
-}
-
-// Sift-up shared by addtree / updtree (ATR:122-137, 159-174).
-ALI_DEV void ali_sift_up(AliSeqGrid &g, int iz, int ix, int tpc)
+// Sift-up shared by addtree / updtree (ATR:122-137, 159-174): the reference swaps the entry at
+// tpc with its parent while T(iz, ix) is smaller than the parent's time.  Here the parents move
+// down into the hole and the entry is stored once at the end (same final arrangement as the chain
+// of swaps); the status writes keep the reference's order, which matters for the nodes that sit
+// in the heap twice.  e0 / k0: the entry at tpc and its key.
+ALI_DEV void ali_sift_up_core(AliSeqGrid &g, unsigned wi_me, double tv, AliHeapEnt e0, double k0, int tpc)
 {
     int tpp = ali_half_round(tpc);
-    double tv = g.tt(iz, ix);
+    bool moved = false;
     while (tpp > 0) {
-        int aa = g.heap[2 * tpp], bb = g.heap[2 * tpp + 1];
-        if (tv < g.tt(aa, bb)) {
-            g.s(iz, ix) = tpp;
-            g.s(aa, bb) = tpc;
-            ali_heap_swap(g, tpc, tpp);
+        const double pk = g.hkey[tpp];
+        if (tv < pk) {
+            const AliHeapEnt pe = g.heap[tpp];
+            g.st[wi_me] = tpp;
+            g.st[pe.wi] = tpc;
+            g.heap[tpc] = pe;
+            g.hkey[tpc] = pk;
             tpc = tpp;
             tpp = ali_half_round(tpc);
+            moved = true;
         } else {
             tpp = 0;
         }
     }
+    if (moved) { g.heap[tpc] = e0; g.hkey[tpc] = k0; }
 }
 
-ALI_DEV void ali_addtree(AliSeqGrid &g, int iz, int ix)
+// updtree (ATR:141-175): called right after T(iz, ix) was rewritten, so the keys of the node's heap
+// entries are refreshed first.  The reference compares through ttn[btg[...]]; keys that always equal
+// T give the same order.
+ALI_DEV void ali_updtree_w(AliSeqGrid &g, int iz, int ix, unsigned wi_me)
+{
+    const unsigned me = ((unsigned)iz << 16) | (unsigned)ix;
+    const int tpc = g.st[wi_me];
+    const double tv = g.tt(iz, ix);
+    const AliHeapEnt e0 = g.heap[tpc];
+    double k0;
+    if (e0.zx == me) { k0 = tv; g.hkey[tpc] = tv; }
+    else k0 = g.hkey[tpc];   // only after the reference's own duplicate-entry mix-ups
+    if (g.ndup > 0) {
+        const bool is_dup = (g.dup0 == me) || (g.ndup > 1 && g.dup1 == me) || (g.ndup > 2 && g.dup2 == me) ||
+                            (g.ndup > 3 && g.dup3 == me);
+        if (is_dup)
+            for (int q = 1; q <= g.ntr; q++)
+                if (g.heap[q].zx == me) g.hkey[q] = tv;
+    }
+    ali_sift_up_core(g, wi_me, tv, e0, k0, tpc);
+}
+
+ALI_DEV void ali_updtree(AliSeqGrid &g, int iz, int ix) { ali_updtree_w(g, iz, ix, (unsigned)g.widx(iz, ix)); }
+
+// addtree (ATR:106-138).
+ALI_DEV void ali_addtree_w(AliSeqGrid &g, int iz, int ix, unsigned wi_me)
 {
     if (g.ntr + 2 >= g.heap_cap) { g.overflow = 1; return; }
+    const unsigned me = ((unsigned)iz << 16) | (unsigned)ix;
+    const double tv = g.tt(iz, ix);
+    if (g.st[wi_me] > 0) {   // second heap entry for a node (the reference pushes the seed corners twice)
+        if (g.ndup == 0) g.dup0 = me; else if (g.ndup == 1) g.dup1 = me; else if (g.ndup == 2) g.dup2 = me;
+        else if (g.ndup == 3) g.dup3 = me; else { g.overflow = 1; return; }
+        g.ndup++;
+        for (int q = 1; q <= g.ntr; q++)
+            if (g.heap[q].zx == me) g.hkey[q] = tv;
+    }
     g.ntr += 1;
-    g.s(iz, ix) = g.ntr;
-    g.heap[2 * g.ntr] = iz;
-    g.heap[2 * g.ntr + 1] = ix;
-    ali_sift_up(g, iz, ix, g.ntr);
+    AliHeapEnt e0;
+    e0.zx = me; e0.wi = wi_me;
+    g.st[wi_me] = g.ntr;
+    g.heap[g.ntr] = e0;
+    g.hkey[g.ntr] = tv;
+    ali_sift_up_core(g, wi_me, tv, e0, tv, g.ntr);
 }
 
-ALI_DEV void ali_updtree(AliSeqGrid &g, int iz, int ix) { ali_sift_up(g, iz, ix, g.s(iz, ix)); }
+ALI_DEV void ali_addtree(AliSeqGrid &g, int iz, int ix) { ali_addtree_w(g, iz, ix, (unsigned)g.widx(iz, ix)); }
 
-// ATR:178-237.
+// downtree (ATR:178-237): the last entry replaces the root and sinks; children move up into the
+// hole, the entry is stored once at the end.
 ALI_DEV void ali_downtree(AliSeqGrid &g)
 {
     int ntr = g.ntr;
     if (ntr == 1) { g.ntr = 0; return; }
-    g.s(g.heap[2 * ntr], g.heap[2 * ntr + 1]) = 1;
-    g.heap[2] = g.heap[2 * ntr];
-    g.heap[3] = g.heap[2 * ntr + 1];
+    const AliHeapEnt le = g.heap[ntr];
+    const double kv = g.hkey[ntr];
+    g.st[le.wi] = 1;
+    g.heap[1] = le;
+    g.hkey[1] = kv;
     ntr -= 1;
     int tpp = 1, tpc = 2;
+    bool moved = false;
     while (tpc < ntr) {
-        double rd1 = g.tt(g.heap[2 * tpc], g.heap[2 * tpc + 1]);
-        double rd2 = g.tt(g.heap[2 * tpc + 2], g.heap[2 * tpc + 3]);
+        double rd1 = g.hkey[tpc];
+        const double rd2 = g.hkey[tpc + 1];
         if (rd1 > rd2) { tpc += 1; rd1 = rd2; }
-        rd2 = g.tt(g.heap[2 * tpp], g.heap[2 * tpp + 1]);
-        if (rd1 < rd2) {
-            g.s(g.heap[2 * tpp], g.heap[2 * tpp + 1]) = tpc;
-            g.s(g.heap[2 * tpc], g.heap[2 * tpc + 1]) = tpp;
-            ali_heap_swap(g, tpc, tpp);
+        if (rd1 < kv) {
+            const AliHeapEnt ce = g.heap[tpc];
+            g.st[le.wi] = tpc;
+            g.st[ce.wi] = tpp;
+            g.heap[tpp] = ce;
+            g.hkey[tpp] = rd1;
             tpp = tpc;
             tpc = 2 * tpp;
+            moved = true;
         } else {
             tpc = ntr + 1;
         }
     }
     if (tpc == ntr) {
-        double rd1 = g.tt(g.heap[2 * tpc], g.heap[2 * tpc + 1]);
-        double rd2 = g.tt(g.heap[2 * tpp], g.heap[2 * tpp + 1]);
-        if (rd1 < rd2) {
-            g.s(g.heap[2 * tpp], g.heap[2 * tpp + 1]) = tpc;
-            g.s(g.heap[2 * tpc], g.heap[2 * tpc + 1]) = tpp;
-            ali_heap_swap(g, tpc, tpp);
+        const double rd1 = g.hkey[tpc];
+        if (rd1 < kv) {
+            const AliHeapEnt ce = g.heap[tpc];
+            g.st[le.wi] = tpc;
+            g.st[ce.wi] = tpp;
+            g.heap[tpp] = ce;
+            g.hkey[tpp] = rd1;
+            tpp = tpc;
+            moved = true;
         }
     }
+    if (moved) { g.heap[tpp] = le; g.hkey[tpp] = kv; }
     g.ntr = ntr;
 }
 
@@ -163,7 +229,7 @@ ALI_DEV int ali_seq_march(AliSeqGrid &g, const AliModel &m, int cx, int cz, int 
     int why = ALI_SEQ_EMPTY;
     const int nnx = g.nx, nnz = g.nz;
     while (g.ntr > 0 && !finished) {
-        const int ix = g.heap[3], iz = g.heap[2];
+        const int ix = ALI_ENT_X(g.heap[1]), iz = ALI_ENT_Z(g.heap[1]);
         long long c0 = ALI_CLOCK();
         g.s(iz, ix) = 0;
         ali_downtree(g);
@@ -227,16 +293,17 @@ ALI_DEV int ali_seq_march(AliSeqGrid &g, const AliModel &m, int cx, int cz, int 
 // ---------------------------------------------------------------------------
 struct AliCoopState {
     int have_p, iz, ix, s;       // popped node whose neighbours are being visited, next neighbour
+    unsigned wi;                 // its window index
     int miss, mz, mx, mnnz;      // evaluation lane 0 is waiting for
     int miss_ready, miss_fb;
     double miss_v;
     int finished, why;
 };
 
-ALI_DEV void ali_seq_invalidate(const AliSeqGrid &g, int z, int x)
+ALI_DEV void ali_seq_invalidate(const AliSeqGrid &g, int z, int x, unsigned wi)
 {
     if (z - 2 >= g.wz0 && z + 2 < g.wz0 + g.wnz && x - 2 >= g.wx0 && x + 2 < g.wx0 + g.wnx) {
-        uint8_t *f = g.cf + g.widx(z, x);
+        uint8_t *f = g.cf + wi;
         const int w = g.wnx;
         f[-2 * w] = 0; f[-w - 1] = 0; f[-w] = 0; f[-w + 1] = 0;
         f[-2] = 0; f[-1] = 0; f[1] = 0; f[2] = 0;
@@ -250,38 +317,57 @@ ALI_DEV void ali_seq_invalidate(const AliSeqGrid &g, int z, int x)
     }
 }
 
-#define ALI_COOP_HEAP_POSITIONS 8
-// One lane's share of an evaluation step.  ntr: current heap size (lane 0's value).
-ALI_DEV int ali_coop_step(const AliSeqGrid &g, const AliModel &m, AliCoopState &cs, int lane, int ntr)
+// Speculation looks at the neighbours of the first ALI_COOP_HEAP_POSITIONS heap entries (the
+// likely next pops).  wanted(hp): 4-bit mask of the directions (x-1, x+1, z-1, z+1) whose node is
+// not alive and has no valid cached update.
+#ifndef ALI_COOP_HEAP_POSITIONS
+#define ALI_COOP_HEAP_POSITIONS 32
+#endif
+ALI_DEV unsigned ali_coop_wanted(const AliSeqGrid &g, int hp, int ntr)
+{
+    unsigned mask = 0;
+    if (hp <= ntr && hp <= ALI_COOP_HEAP_POSITIONS) {
+        const AliHeapEnt he = g.heap[hp];
+        const int pz = ALI_ENT_Z(he), px = ALI_ENT_X(he);
+#pragma unroll
+        for (int dir = 0; dir < 4; dir++) {
+            const int cz = pz + (dir == 2 ? -1 : dir == 3 ? 1 : 0), cx = px + (dir == 0 ? -1 : dir == 1 ? 1 : 0);
+            const unsigned wi = he.wi + (unsigned)(dir == 0 ? -1 : dir == 1 ? 1 : dir == 2 ? -g.wnx : g.wnx);
+            if (cz >= 0 && cz < g.nz && cx >= 0 && cx < g.nx && g.in_win(cz, cx) && g.st[wi] != 0 && g.cf[wi] == 0)
+                mask |= 1u << dir;
+        }
+    }
+    return mask;
+}
+
+// True if (cz, cx) is worth evaluating ahead: inside, not alive, no valid cached update.
+ALI_DEV bool ali_coop_wanted_node(const AliSeqGrid &g, int cz, int cx)
+{
+    return cz >= 0 && cz < g.nz && cx >= 0 && cx < g.nx && g.in_win(cz, cx) && g.s(cz, cx) != 0 &&
+           g.cf[g.widx(cz, cx)] == 0;
+}
+
+// One lane's evaluation in a step: lane 0 serves the pending miss (serve), the others evaluate
+// the node they were assigned, if any, into the cache.
+ALI_DEV int ali_coop_step(const AliSeqGrid &g, const AliModel &m, AliCoopState &cs, bool serve, bool has_cand, int cz,
+                          int cx)
 {
     const int nnx = g.nx, nnz = g.nz;
-    int cz = 0, cx = 0, cnnz = nnz;
-    bool want = false;
-    const bool serve = (lane == 0 && cs.miss);
+    int cnnz = nnz;
     if (serve) {
         cz = cs.mz; cx = cs.mx; cnnz = cs.mnnz;
-        want = true;
-    } else {
-        const int slot = lane == 0 ? 4 * ALI_COOP_HEAP_POSITIONS - 1 : lane - 1;
-        const int hp = 1 + (slot >> 2), dir = slot & 3;
-        if (hp <= ntr && hp <= ALI_COOP_HEAP_POSITIONS) {
-            cz = g.heap[2 * hp]; cx = g.heap[2 * hp + 1];
-            if (dir == 0) cx -= 1; else if (dir == 1) cx += 1; else if (dir == 2) cz -= 1; else cz += 1;
-            if (cz >= 0 && cz < nnz && cx >= 0 && cx < nnx && g.in_win(cz, cx))
-                want = g.s(cz, cx) != 0 && g.cf[g.widx(cz, cx)] == 0;
-        }
+    } else if (!has_cand) {
+        return 0;
     }
-    if (want) {
-        int fb = 0;
-        const double v = ali_eval_node(m, g.mv, g, cz, cx, cnnz, nnx, nnz, nnx, g.dnx, &fb);
-        if (serve) {
-            cs.miss_v = v; cs.miss_fb = fb; cs.miss_ready = 1; cs.miss = 0;
-        } else if (!fb) {
-            g.cv[g.widx(cz, cx)] = v;
-            g.cf[g.widx(cz, cx)] = 1;
-        }
+    int fb = 0;
+    const double v = ali_eval_node(m, g.mv, g, cz, cx, cnnz, nnx, nnz, nnx, g.dnx, &fb);
+    if (serve) {
+        cs.miss_v = v; cs.miss_fb = fb; cs.miss_ready = 1; cs.miss = 0;
+    } else if (!fb) {
+        g.cv[g.widx(cz, cx)] = v;
+        g.cf[g.widx(cz, cx)] = 1;
     }
-    return want ? 1 : 0;
+    return 1;
 }
 
 // Lane 0: the reference's loop (same order of heap operations as ali_seq_march) until it ends
@@ -293,8 +379,9 @@ ALI_DEV int ali_coop_advance(AliSeqGrid &g, AliCoopState &cs, int cx, int cz, in
     for (;;) {
         if (!cs.have_p) {
             if (g.ntr <= 0 || cs.finished) return 1;
-            cs.ix = g.heap[3]; cs.iz = g.heap[2];
-            g.s(cs.iz, cs.ix) = 0;
+            const AliHeapEnt top = g.heap[1];
+            cs.ix = ALI_ENT_X(top); cs.iz = ALI_ENT_Z(top); cs.wi = top.wi;
+            g.st[top.wi] = 0;
             ali_downtree(g);
             cnt.pops++;
             cs.s = 0;
@@ -308,10 +395,10 @@ ALI_DEV int ali_coop_advance(AliSeqGrid &g, AliCoopState &cs, int cx, int cz, in
             const bool inside = (s < 2) ? (0 <= x && x <= nnx - 1) : (0 <= z && z <= nnz - 1);
             if (inside) {
                 if (!g.in_win(z, x)) { cs.finished = 1; cs.why = ALI_SEQ_LIMIT; continue; }
-                const int32_t stv = g.s(z, x);
+                const unsigned wi = cs.wi + (unsigned)(s == 0 ? -1 : s == 1 ? 1 : s == 2 ? -g.wnx : g.wnx);
+                const int32_t stv = g.st[wi];
                 if (stv != 0) {
                     const int nnz_l = (nnz_bug && s < 2 && stv > 0) ? nnx : nnz;
-                    const size_t wi = g.widx(z, x);
                     double v;
                     int fb = 0;
                     if (cs.miss_ready) { v = cs.miss_v; fb = cs.miss_fb; cs.miss_ready = 0; }
@@ -321,11 +408,11 @@ ALI_DEV int ali_coop_advance(AliSeqGrid &g, AliCoopState &cs, int cx, int cz, in
                     cnt.fallbacks += fb;
                     const bool changed = (stv == -1) || !(g.tt(z, x) == v);
                     g.tref(z, x) = v;
-                    if (changed) ali_seq_invalidate(g, z, x);
+                    if (changed) ali_seq_invalidate(g, z, x, wi);
                     if (nnz_l == nnz && !fb) { g.cv[wi] = v; g.cf[wi] = 1; }
                     else g.cf[wi] = 0;
-                    if (stv == -1) ali_addtree(g, z, x);
-                    else ali_updtree(g, z, x);
+                    if (stv == -1) ali_addtree_w(g, z, x, wi);
+                    else ali_updtree_w(g, z, x, wi);
                 }
             } else if (max_dist >= 0) {
                 int d = (s < 2) ? (cx - x) : (cz - z);
@@ -346,9 +433,12 @@ ALI_DEV int ali_coop_advance(AliSeqGrid &g, AliCoopState &cs, int cx, int cz, in
 
 // Same contract as ali_seq_march; every lane of the warp calls it (the host replay passes
 // nlanes and plays the lanes one after the other).  Only lane 0's g / cnt are meaningful.
-ALI_DEV int ali_seq_march_coop(AliSeqGrid &g, const AliModel &m, int cx, int cz, int max_dist, int nnz_bug,
-                               int stop_r, AliSeqCounters &cnt, int lane, int nlanes)
+ALI_DEV int ali_seq_march_coop(AliSeqGrid &g_mem, const AliModel &m, int cx, int cz, int max_dist, int nnz_bug,
+                               int stop_r, AliSeqCounters &cnt_mem, int lane, int nlanes)
 {
+    // the caller's grid sits in an array of the source state (local memory): work on register copies
+    AliSeqGrid g = g_mem;
+    AliSeqCounters cnt = cnt_mem;
     AliCoopState cs;
     cs.have_p = 0; cs.iz = cs.ix = cs.s = 0;
     cs.miss = 0; cs.mz = cs.mx = cs.mnnz = 0;
@@ -357,24 +447,97 @@ ALI_DEV int ali_seq_march_coop(AliSeqGrid &g, const AliModel &m, int cx, int cz,
     for (;;) {
         int done = 0;
 #if defined(__CUDA_ARCH__)
+        const long long c0 = ALI_CLOCK();
         const int ntr = __shfl_sync(0xffffffffu, g.ntr, 0);
-        const int did = ali_coop_step(g, m, cs, lane, ntr);
+        const int serve = __shfl_sync(0xffffffffu, cs.miss, 0);
+        // candidates of heap positions 1..32 (4 bits each), packed 8 positions per word
+        unsigned w4 = ali_coop_wanted(g, lane + 1, ntr) << (4 * (lane & 7));
+        w4 |= __shfl_xor_sync(0xffffffffu, w4, 1);
+        w4 |= __shfl_xor_sync(0xffffffffu, w4, 2);
+        w4 |= __shfl_xor_sync(0xffffffffu, w4, 4);
+        unsigned words[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) words[q] = __shfl_sync(0xffffffffu, w4, 8 * q);
+        // a step that serves a miss reserves lanes 1..3 for the neighbours of the popped node that
+        // are still to be visited (the popped node has left the heap); the remaining lanes take the
+        // candidates in heap order
+        const int pz = __shfl_sync(0xffffffffu, cs.iz, 0), px = __shfl_sync(0xffffffffu, cs.ix, 0);
+        const int ps = __shfl_sync(0xffffffffu, cs.s, 0);
+        int j = serve ? lane - 4 : lane;
+        bool has = false;
+        int cz_c = 0, cx_c = 0;
+        if (serve && lane >= 1 && lane <= 3) {
+            const int d = ps + lane;
+            if (d < 4) {
+                cz_c = pz + (d == 2 ? -1 : d == 3 ? 1 : 0); cx_c = px + (d == 0 ? -1 : d == 1 ? 1 : 0);
+                has = ali_coop_wanted_node(g, cz_c, cx_c);
+            }
+        }
+        if (j >= 0) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int c = __popc(words[q]);
+                if (!has) {
+                    if (j < c) {
+                        const int bit = (int)__fns(words[q], 0, j + 1);
+                        const int hp = 8 * q + (bit >> 2) + 1, dir = bit & 3;
+                        const AliHeapEnt he = g.heap[hp];
+                        cz_c = ALI_ENT_Z(he) + (dir == 2 ? -1 : dir == 3 ? 1 : 0);
+                        cx_c = ALI_ENT_X(he) + (dir == 0 ? -1 : dir == 1 ? 1 : 0);
+                        has = true;
+                        j = -1000;
+                    } else {
+                        j -= c;
+                    }
+                }
+            }
+        }
+        const int did = ali_coop_step(g, m, cs, serve && lane == 0, has, cz_c, cx_c);
         const unsigned mask = __ballot_sync(0xffffffffu, did);
         if (lane == 0) {
+            const long long c1 = ALI_CLOCK();
             cnt.steps++;
             cnt.computed += __popc(mask);
             done = ali_coop_advance(g, cs, cx, cz, max_dist, nnz_bug, stop_r, cnt);
+            cnt.cyc_eval += c1 - c0;
+            cnt.cyc_heap += ALI_CLOCK() - c1;
         }
         __syncwarp();
         done = __shfl_sync(0xffffffffu, done, 0);
 #else
         (void)lane;
         cnt.steps++;
-        for (int l = 0; l < nlanes; l++) cnt.computed += ali_coop_step(g, m, cs, l, g.ntr);
+        {
+            // the lanes pick their nodes from the same snapshot: collect first, evaluate after
+            int cz_c[32], cx_c[32], nc = 0, used = 0;
+            const bool serve = cs.miss != 0;
+            if (serve) {
+                used = 4;
+                for (int d = cs.s + 1; d < 4; d++) {
+                    const int z = cs.iz + (d == 2 ? -1 : d == 3 ? 1 : 0), x = cs.ix + (d == 0 ? -1 : d == 1 ? 1 : 0);
+                    if (ali_coop_wanted_node(g, z, x)) { cz_c[nc] = z; cx_c[nc] = x; nc++; }
+                }
+            }
+            int taken = 0;
+            for (int hp = 1; hp <= ALI_COOP_HEAP_POSITIONS && used + taken < nlanes; hp++) {
+                const unsigned wm = ali_coop_wanted(g, hp, g.ntr);
+                for (int dir = 0; dir < 4 && used + taken < nlanes; dir++)
+                    if (wm & (1u << dir)) {
+                        cz_c[nc] = ALI_ENT_Z(g.heap[hp]) + (dir == 2 ? -1 : dir == 3 ? 1 : 0);
+                        cx_c[nc] = ALI_ENT_X(g.heap[hp]) + (dir == 0 ? -1 : dir == 1 ? 1 : 0);
+                        nc++; taken++;
+                    }
+            }
+            if (serve) cnt.computed += ali_coop_step(g, m, cs, true, false, 0, 0);
+            for (int q = 0; q < nc; q++) cnt.computed += ali_coop_step(g, m, cs, false, true, cz_c[q], cx_c[q]);
+        }
         done = ali_coop_advance(g, cs, cx, cz, max_dist, nnz_bug, stop_r, cnt);
 #endif
         if (done) break;
     }
+    g_mem.ntr = g.ntr; g_mem.overflow = g.overflow; g_mem.ndup = g.ndup;
+    g_mem.dup0 = g.dup0; g_mem.dup1 = g.dup1; g_mem.dup2 = g.dup2; g_mem.dup3 = g.dup3;
+    cnt_mem = cnt;
     if (!cs.finished) cs.why = ALI_SEQ_EMPTY;
     return cs.why;
 }
@@ -387,9 +550,13 @@ ALI_DEV void ali_seq_clear(AliSeqGrid &g, bool clear_t, int lane, int nlanes)
     if (g.cf)
         for (size_t i = lane; i < n; i += nlanes) g.cf[i] = 0;
     if (clear_t)
-        for (size_t i = lane; i < n; i += nlanes) g.t[i] = 0.0; // level grids only (window == grid)
+        for (size_t i = lane; i < n; i += nlanes) {   // level grids only (window == grid); NaN = no estimate
+            const unsigned long long nanbits = 0xFFFFFFFFFFFFFFFFull;
+            memcpy(&g.t[i], &nanbits, sizeof(double));
+        }
     g.ntr = 0;
     g.overflow = 0;
+    g.ndup = 0;
 }
 
 // Analytic straight-ray seed of the source's own coarse cell (ATR:1546-1590 with
@@ -434,8 +601,10 @@ ALI_DEV void ali_seq_seed_push(AliSeqGrid &g1, int cz1, int cx1, int side1)
 // Every-third-node injection of grid a into the 3x coarser grid b (ATR:1719-1753,
 // 1887-1921, 2006-2040, 2391-2425, 2725-2759).  Single lane: the heap insertion order
 // is part of the result.
-ALI_DEV void ali_seq_handoff(const AliSeqGrid &a, int cza, int cxa, AliSeqGrid &b, int czb, int cxb)
+ALI_DEV void ali_seq_handoff(const AliSeqGrid &a_mem, int cza, int cxa, AliSeqGrid &b_mem, int czb, int cxb)
 {
+    const AliSeqGrid a = a_mem;   // register copies (see ali_seq_march_coop)
+    AliSeqGrid b = b_mem;
     for (int i = 0; i <= a.nz - 1; i += 3) {
         for (int j = 0; j <= a.nx - 1; j += 3) {
             int pz = czb + (i - cza) / 3;
@@ -455,6 +624,8 @@ ALI_DEV void ali_seq_handoff(const AliSeqGrid &a, int cza, int cxa, AliSeqGrid &
             }
         }
     }
+    b_mem.ntr = b.ntr; b_mem.overflow = b.overflow; b_mem.ndup = b.ndup;
+    b_mem.dup0 = b.dup0; b_mem.dup1 = b.dup1; b_mem.dup2 = b.dup2; b_mem.dup3 = b.dup3;
 }
 
 // ---------------------------------------------------------------------------
@@ -509,7 +680,8 @@ ALI_HD size_t ali_plan_max_level_nodes(const AliSourcePlan &p)
 struct AliSeqScratch {
     double *tA, *tB;     // level T buffers (ping-pong), each max_level_nodes
     int32_t *sA, *sB;    // level status buffers; sB is re-used for the main-grid window
-    int32_t *heap;       // 2 * heap_cap
+    AliHeapEnt *heap;    // heap_cap entries
+    double *hkey;        // heap_cap
     double *cval;        // evaluation cache of the grid being marched (status_cap entries), or nullptr
     uint8_t *cflag;
     int heap_cap;
@@ -565,7 +737,7 @@ ALI_DEV void ali_src_level_geometry(AliSrcState &s, const AliModel &m, const Ali
     g.st = cur == 0 ? sc.sA : sc.sB;
     g.t_stride = g.nx;
     g.wz0 = 0; g.wx0 = 0; g.wnz = g.nz; g.wnx = g.nx;
-    g.heap = sc.heap; g.heap_cap = sc.heap_cap;
+    g.heap = sc.heap; g.heap_cap = sc.heap_cap; g.hkey = sc.hkey;
     g.cv = sc.cval; g.cf = sc.cflag;
     g.mv = ali_make_view(scl, bottom, left, p.fine ? p.sg : 1, 1);
     g.dnx = m.dnx / scl;
@@ -631,7 +803,7 @@ ALI_DEV void ali_src_main_geometry(AliSrcState &s, const AliModel &m, const AliS
     mg.wz0 = ali_imax(0, p.isz - half); mg.wx0 = ali_imax(0, p.isx - half);
     mg.wnz = ali_imin(p.nz - 1, p.isz + half) - mg.wz0 + 1;
     mg.wnx = ali_imin(p.nx - 1, p.isx + half) - mg.wx0 + 1;
-    mg.heap = sc.heap; mg.heap_cap = sc.heap_cap;
+    mg.heap = sc.heap; mg.heap_cap = sc.heap_cap; mg.hkey = sc.hkey;
     mg.cv = sc.cval; mg.cf = sc.cflag;
     mg.mv = s.base;
     mg.dnx = m.dnx;

@@ -67,6 +67,7 @@ struct AliBatch {
     double *seq_t;          // [n_src][2*seq_cap]
     int32_t *seq_s;         // [n_src][2*seq_cap]
     int32_t *seq_heap;      // [n_src][2*heap_cap]
+    double *seq_hkey;       // [n_src][heap_cap] travel times of the heap entries
     double *seq_cval;       // [n_src][seq_cap] evaluation cache of the cooperative march
     uint8_t *seq_cflag;     // [n_src][seq_cap]
     size_t seq_cap;
@@ -107,7 +108,7 @@ __global__ void ali_vmax_kernel(AliModel m, unsigned long long *out_bits)
     if ((threadIdx.x & 31) == 0) atomicMax(out_bits, (unsigned long long)__double_as_longlong(best));
 }
 
-__global__ void __launch_bounds__(32) ali_seq_kernel(AliBatch b)
+__global__ void __launch_bounds__(32, 1) ali_seq_kernel(AliBatch b)
 {
     const int src = blockIdx.x;
     const int lane = threadIdx.x;
@@ -119,7 +120,8 @@ __global__ void __launch_bounds__(32) ali_seq_kernel(AliBatch b)
     sc.tB = sc.tA + b.seq_cap;
     sc.sA = b.seq_s + (size_t)src * 2 * b.seq_cap;
     sc.sB = sc.sA + b.seq_cap;
-    sc.heap = b.seq_heap + (size_t)src * 2 * b.heap_cap;
+    sc.heap = reinterpret_cast<AliHeapEnt *>(b.seq_heap) + (size_t)src * b.heap_cap;
+    sc.hkey = b.seq_hkey + (size_t)src * b.heap_cap;
     sc.cval = b.seq_cval + (size_t)src * b.seq_cap;
     sc.cflag = b.seq_cflag + (size_t)src * b.seq_cap;
     sc.heap_cap = b.heap_cap;
@@ -718,7 +720,7 @@ struct alifmm_ctx {
     int band_smem_bytes = 0;   // measured on B200: L1 for the T / status gathers is worth more than smem lists
     // resident batch
     int n_slots = 0, sg = 0, fz = 0, fx = 0;
-    DevBuf T, st, seq_t, seq_s, seq_heap, seq_cval, seq_cflag, lists, stage, rec, jobs, ray_x, ray_y, ray_time, ray_len, ray_flag, misc;
+    DevBuf T, st, seq_t, seq_s, seq_heap, seq_hkey, seq_cval, seq_cflag, lists, stage, rec, jobs, ray_x, ray_y, ray_time, ray_len, ray_flag, misc;
     alifmm_counters_t cnt{};
 };
 
@@ -765,7 +767,7 @@ extern "C" void alifmm_destroy(alifmm_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (void *p : c->model_allocs) cudaFree(p);
-    DevBuf *bufs[] = {&c->T, &c->st, &c->seq_t, &c->seq_s, &c->seq_heap, &c->seq_cval, &c->seq_cflag, &c->lists, &c->stage, &c->rec, &c->jobs,
+    DevBuf *bufs[] = {&c->T, &c->st, &c->seq_t, &c->seq_s, &c->seq_heap, &c->seq_hkey, &c->seq_cval, &c->seq_cflag, &c->lists, &c->stage, &c->rec, &c->jobs,
                       &c->ray_x, &c->ray_y, &c->ray_time, &c->ray_len, &c->ray_flag, &c->misc};
     for (DevBuf *b : bufs) dev_release(*b);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
@@ -950,6 +952,7 @@ static int ttf_attempt(alifmm_ctx *c, int32_t n_src, const int32_t *src_iz, cons
     if ((rc = dev_reserve(c->seq_t, (size_t)n_src * 2 * b.seq_cap * sizeof(double))) != 0) return rc;
     if ((rc = dev_reserve(c->seq_s, (size_t)n_src * 2 * b.seq_cap * sizeof(int32_t))) != 0) return rc;
     if ((rc = dev_reserve(c->seq_heap, (size_t)n_src * 2 * b.heap_cap * sizeof(int32_t))) != 0) return rc;
+    if ((rc = dev_reserve(c->seq_hkey, (size_t)n_src * b.heap_cap * sizeof(double))) != 0) return rc;
     if ((rc = dev_reserve(c->seq_cval, (size_t)n_src * b.seq_cap * sizeof(double))) != 0) return rc;
     if ((rc = dev_reserve(c->seq_cflag, (size_t)n_src * b.seq_cap + 16)) != 0) return rc;
     if ((rc = dev_reserve(c->lists, (size_t)n_src * 4 * b.band_cap * sizeof(unsigned))) != 0) return rc;
@@ -957,7 +960,7 @@ static int ttf_attempt(alifmm_ctx *c, int32_t n_src, const int32_t *src_iz, cons
     if ((rc = dev_reserve(c->rec, (size_t)n_src * sizeof(AliSourceRec))) != 0) return rc;
     b.T = (double *)c->T.p; b.st = (uint8_t *)c->st.p;
     b.seq_t = (double *)c->seq_t.p; b.seq_s = (int32_t *)c->seq_s.p; b.seq_heap = (int32_t *)c->seq_heap.p;
-    b.seq_cval = (double *)c->seq_cval.p; b.seq_cflag = (uint8_t *)c->seq_cflag.p;
+    b.seq_hkey = (double *)c->seq_hkey.p; b.seq_cval = (double *)c->seq_cval.p; b.seq_cflag = (uint8_t *)c->seq_cflag.p;
     b.lists = (unsigned *)c->lists.p; b.stage = (double *)c->stage.p; b.rec = (AliSourceRec *)c->rec.p;
 
     std::vector<AliSourceRec> recs(n_src);
@@ -1026,9 +1029,9 @@ static int ttf_attempt(alifmm_ctx *c, int32_t n_src, const int32_t *src_iz, cons
     }
     if (getenv("ALIFMM_DEBUG")) {
         const AliSourceRec &r = recs[0];
-        fprintf(stderr, "[alifmm] source 0 seq: pops %lld evals %lld, steps %lld computed %lld, cycles/pop heap %.0f eval %.0f\n", r.seq.cnt.pops,
+        fprintf(stderr, "[alifmm] source 0 seq: pops %lld evals %lld, steps %lld computed %lld, cycles/pop walk %.0f, cycles/step %.0f\n", r.seq.cnt.pops,
                 r.seq.cnt.evals, r.seq.cnt.steps, r.seq.cnt.computed, (double)r.seq.cnt.cyc_heap / (r.seq.cnt.pops + 1e-9),
-                (double)r.seq.cnt.cyc_eval / (r.seq.cnt.pops + 1e-9));
+                (double)r.seq.cnt.cyc_eval / (r.seq.cnt.steps + 1e-9));
         fprintf(stderr, "[alifmm] source 0: rounds %lld, cycles/round A %.0f B %.0f C %.0f sort %.0f, evals/round %.0f, band max %lld\n",
                 r.rounds, (double)r.cycles[0] / (r.rounds + 1e-9), (double)r.cycles[1] / (r.rounds + 1e-9),
                 (double)r.cycles[2] / (r.rounds + 1e-9), (double)r.cycles[3] / (r.rounds + 1e-9),

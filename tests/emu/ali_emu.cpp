@@ -214,7 +214,9 @@ extern "C" int emu_ttf(int nz, int nx, const double *veln, const int32_t *velpn,
     std::vector<int32_t> sA(cap), sB(cap), heap(2 * (cap / 2 + 64));
     AliSeqScratch sc;
     sc.tA = tA.data(); sc.tB = tB.data(); sc.sA = sA.data(); sc.sB = sB.data();
-    sc.heap = heap.data(); sc.heap_cap = (int)(cap / 2 + 64); sc.status_cap = cap;
+    sc.heap = reinterpret_cast<AliHeapEnt *>(heap.data()); sc.heap_cap = (int)(cap / 2 + 64); sc.status_cap = cap;
+    std::vector<double> hkey(cap / 2 + 64);
+    sc.hkey = hkey.data();
     std::vector<double> cval(g_coop_lanes > 0 ? cap : 0);
     std::vector<uint8_t> cflag(g_coop_lanes > 0 ? cap : 0);
     sc.cval = g_coop_lanes > 0 ? cval.data() : nullptr;
