@@ -423,7 +423,7 @@ class ALI_FMM:
         cap = 5 * (veln.shape[0] + veln.shape[1])
         if save_rays:
             self.ray_paths_x = np.zeros((n_trans, n_trans, cap))
-            self.ray_paths_y = np.copy(self.ray_paths_x)
+            self.ray_paths_y = np.zeros((n_trans, n_trans, cap))
             self.ray_len = np.zeros((n_trans, n_trans), dtype=int)
         self.ray_flags = np.zeros((n_trans, n_trans), dtype=int)
         if type(trans_pairs) == type(None):
@@ -464,18 +464,21 @@ class ALI_FMM:
                         c_ray = None
                         if ray_i:
                             siz, six = self._source_nodes(ray_i)
-                            x, y, ln, tm, fl = ctx.rays(siz, six, ray_slot, cap, want_paths=save_rays)
+                            ri = np.asarray(ray_i)
+                            rj = np.asarray(part)[np.asarray(ray_slot)]
+                            if save_rays:
+                                # the library writes each path straight into ray_paths_x / ray_paths_y
+                                # (coarse-cell units, ATR:4355-4356)
+                                ln, tm, fl = ctx.rays_into(siz, six, ray_slot, cap, subgrid_size, ri * n_trans + rj,
+                                                           self.ray_paths_x, self.ray_paths_y)
+                            else:
+                                _, _, ln, tm, fl = ctx.rays(siz, six, ray_slot, cap, want_paths=False)
                             c_ray = ctx.counters()
                             with lock:
-                                for r, (i, slot) in enumerate(zip(ray_i, ray_slot)):
-                                    j = part[slot]
-                                    times[i, j] = tm[r]
-                                    self.ray_flags[i, j] = fl[r]
-                                    if save_rays:
-                                        n = int(ln[r])
-                                        self.ray_paths_x[i, j, 0:n] = x[r, 0:n] / subgrid_size   # ATR:4355-4356
-                                        self.ray_paths_y[i, j, 0:n] = y[r, 0:n] / subgrid_size
-                                        self.ray_len[i, j] = n
+                                times[ri, rj] = tm
+                                self.ray_flags[ri, rj] = fl
+                                if save_rays:
+                                    self.ray_len[ri, rj] = ln
                                 bar_ray.update(len(ray_i))
                         agg = _merge_counters(agg, c_ttf, c_ray)
                     counters[d] = agg

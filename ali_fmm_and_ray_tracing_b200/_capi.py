@@ -43,7 +43,8 @@ class Counters(ctypes.Structure):
 
 EXPORTS = [
     "alifmm_device_count", "alifmm_create", "alifmm_destroy", "alifmm_set_option", "alifmm_set_stream",
-    "alifmm_ttf", "alifmm_ttf_fetch", "alifmm_ttf_shape", "alifmm_rays", "alifmm_mem_info", "alifmm_counters",
+    "alifmm_ttf", "alifmm_ttf_fetch", "alifmm_ttf_shape", "alifmm_rays", "alifmm_rays_into", "alifmm_trim",
+    "alifmm_mem_info", "alifmm_counters",
     "alifmm_velocity_curves", "alifmm_min_max_vel", "alifmm_last_error",
 ]
 
@@ -76,6 +77,9 @@ def load():
     lib.alifmm_ttf_shape.argtypes = [vp, _i32p, _i32p, _i32p, _i32p]
     lib.alifmm_rays.argtypes = [vp, ctypes.c_int32, _i32p, _i32p, _i32p, ctypes.c_int32, _f64p, _f64p, _i32p, _f64p,
                                 _i32p]
+    lib.alifmm_rays_into.argtypes = [vp, ctypes.c_int32, _i32p, _i32p, _i32p, ctypes.c_int32, ctypes.c_double, _i64p, _f64p,
+                                     _f64p, _i32p, _f64p, _i32p]
+    lib.alifmm_trim.argtypes = [ctypes.c_int]
     lib.alifmm_mem_info.argtypes = [vp, _i64p, _i64p]
     lib.alifmm_counters.argtypes = [vp, ctypes.POINTER(Counters)]
     lib.alifmm_velocity_curves.argtypes = [vp] + [ctypes.c_double] * 5 + [_f64p, _f64p]
@@ -88,6 +92,11 @@ def load():
 def _check(rc):
     if rc != 0:
         raise AlifmmError(rc, load().alifmm_last_error().decode("utf-8", "replace"))
+
+
+def trim(device=-1):
+    """Releases the device / pinned buffers the library keeps for reuse between contexts."""
+    load().alifmm_trim(int(device))
 
 
 def device_count():
@@ -193,6 +202,28 @@ class Context:
                                      int(capacity), _ptr(x, _f64p), _ptr(y, _f64p), _ptr(ln, _i32p), _ptr(tm, _f64p),
                                      _ptr(fl, _i32p)))
         return x, y, ln, tm, fl
+
+    def rays_into(self, src_iz, src_ix, rec_slot, capacity, divisor, rows, base_x, base_y):
+        """Traces rays and writes ray r (its points divided by ``divisor``) into row ``rows[r]`` of the
+        caller's dense float64 arrays ``base_x`` / ``base_y`` ([..., capacity], C-contiguous).
+        Returns (length, time, flag)."""
+        src_iz = np.ascontiguousarray(src_iz, dtype=np.int32)
+        src_ix = np.ascontiguousarray(src_ix, dtype=np.int32)
+        rec_slot = np.ascontiguousarray(rec_slot, dtype=np.int32)
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        n = len(src_iz)
+        for a in (base_x, base_y):
+            if a.dtype != np.float64 or not a.flags.c_contiguous or a.shape[-1] != capacity:
+                raise ValueError("rays_into: destination must be C-contiguous float64 with last dimension = capacity")
+            if n and int(rows.max()) >= a.size // capacity:
+                raise ValueError("rays_into: row index beyond the destination")
+        ln = np.zeros(n, dtype=np.int32)
+        tm = np.zeros(n)
+        fl = np.zeros(n, dtype=np.int32)
+        _check(self._lib.alifmm_rays_into(self._h, n, _ptr(src_iz, _i32p), _ptr(src_ix, _i32p), _ptr(rec_slot, _i32p),
+                                          int(capacity), float(divisor), _ptr(rows, _i64p), _ptr(base_x, _f64p),
+                                          _ptr(base_y, _f64p), _ptr(ln, _i32p), _ptr(tm, _f64p), _ptr(fl, _i32p)))
+        return ln, tm, fl
 
     def mem_info(self):
         f = ctypes.c_int64()

@@ -18,6 +18,7 @@
 #include <stdlib.h>
 #include <string>
 #include <vector>
+#include <mutex>
 
 #include "../../include/alifmm.h"
 #include "ali_core.cuh"
@@ -720,26 +721,94 @@ struct alifmm_ctx {
     int band_smem_bytes = 0;   // measured on B200: L1 for the T / status gathers is worth more than smem lists
     // resident batch
     int n_slots = 0, sg = 0, fz = 0, fx = 0;
-    DevBuf T, st, seq_t, seq_s, seq_heap, seq_hkey, seq_cval, seq_cflag, lists, stage, rec, jobs, ray_x, ray_y, ray_time, ray_len, ray_flag, misc;
+    DevBuf T, st, seq_t, seq_s, seq_heap, seq_hkey, seq_cval, seq_cflag, lists, stage, rec, jobs, ray_x, ray_y, ray_time, ray_len, ray_flag, ray_off, pack, misc;
     alifmm_counters_t cnt{};
 };
 
+// Large device buffers are recycled through a per-device pool: the reference-facing API creates a
+// context per call (it re-takes the model every time, ATR:3889-3900), and cudaFree / cudaMalloc of
+// the tens of GB a headline batch needs cost 0.7 s per call otherwise.  alifmm_trim() empties it.
+#define ALI_POOL_MIN_BYTES ((size_t)1 << 20)
+struct PoolEntry { void *p; size_t bytes; int device; };
+static std::mutex g_pool_mutex;
+static std::vector<PoolEntry> g_pool;
+
+static size_t pool_bytes(int device)
+{
+    std::lock_guard<std::mutex> lk(g_pool_mutex);
+    size_t n = 0;
+    for (const PoolEntry &e : g_pool) if (e.device == device) n += e.bytes;
+    return n;
+}
+
+static void pool_trim(int device)   // device < 0: all devices
+{
+    std::lock_guard<std::mutex> lk(g_pool_mutex);
+    int cur = -1;
+    cudaGetDevice(&cur);
+    for (size_t i = 0; i < g_pool.size();) {
+        if (device < 0 || g_pool[i].device == device) {
+            cudaSetDevice(g_pool[i].device);
+            cudaFree(g_pool[i].p);
+            g_pool[i] = g_pool.back();
+            g_pool.pop_back();
+        } else {
+            i++;
+        }
+    }
+    if (cur >= 0) cudaSetDevice(cur);
+}
+
+static void dev_give_back(DevBuf &b, int device)
+{
+    if (!b.p) return;
+    if (b.bytes >= ALI_POOL_MIN_BYTES) {
+        std::lock_guard<std::mutex> lk(g_pool_mutex);
+        g_pool.push_back(PoolEntry{b.p, b.bytes, device});
+    } else {
+        cudaFree(b.p);
+    }
+    b.p = nullptr; b.bytes = 0;
+}
+
+// The calling thread's current device must be the context's.
 static int dev_reserve(DevBuf &b, size_t bytes)
 {
     if (b.bytes >= bytes && b.p) return ALIFMM_OK;
-    if (b.p) cudaFree(b.p);
-    b.p = nullptr; b.bytes = 0;
+    int device = 0;
+    cudaGetDevice(&device);
+    dev_give_back(b, device);
+    if (bytes >= ALI_POOL_MIN_BYTES) {
+        // smallest pooled buffer that fits and is not wastefully large
+        std::lock_guard<std::mutex> lk(g_pool_mutex);
+        int best = -1;
+        for (size_t i = 0; i < g_pool.size(); i++)
+            if (g_pool[i].device == device && g_pool[i].bytes >= bytes && g_pool[i].bytes <= bytes + bytes / 4 + (64 << 20) &&
+                (best < 0 || g_pool[i].bytes < g_pool[best].bytes))
+                best = (int)i;
+        if (best >= 0) {
+            b.p = g_pool[best].p; b.bytes = g_pool[best].bytes;
+            g_pool[best] = g_pool.back();
+            g_pool.pop_back();
+            return ALIFMM_OK;
+        }
+    }
     cudaError_t e = cudaMalloc(&b.p, bytes);
-    if (e != cudaSuccess) return fail(ALIFMM_E_CUDA, std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
+    if (e != cudaSuccess) {
+        // the pool may be holding what this allocation needs
+        cudaGetLastError();
+        pool_trim(device);
+        e = cudaMalloc(&b.p, bytes);
+    }
+    if (e != cudaSuccess) {
+        b.p = nullptr;
+        return fail(ALIFMM_E_CUDA, std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
+    }
     b.bytes = bytes;
     return ALIFMM_OK;
 }
 
-static void dev_release(DevBuf &b)
-{
-    if (b.p) cudaFree(b.p);
-    b.p = nullptr; b.bytes = 0;
-}
+static void dev_release(DevBuf &b, int device) { dev_give_back(b, device); }
 
 template <class Tp>
 static int upload(alifmm_ctx *c, const Tp *host, size_t n, const Tp **dev_out)
@@ -768,8 +837,8 @@ extern "C" void alifmm_destroy(alifmm_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (void *p : c->model_allocs) cudaFree(p);
     DevBuf *bufs[] = {&c->T, &c->st, &c->seq_t, &c->seq_s, &c->seq_heap, &c->seq_hkey, &c->seq_cval, &c->seq_cflag, &c->lists, &c->stage, &c->rec, &c->jobs,
-                      &c->ray_x, &c->ray_y, &c->ray_time, &c->ray_len, &c->ray_flag, &c->misc};
-    for (DevBuf *b : bufs) dev_release(*b);
+                      &c->ray_x, &c->ray_y, &c->ray_time, &c->ray_len, &c->ray_flag, &c->ray_off, &c->pack, &c->misc};
+    for (DevBuf *b : bufs) dev_release(*b, c->device);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
@@ -1068,12 +1137,10 @@ extern "C" int alifmm_ttf_fetch(alifmm_ctx *c, int32_t slot, double *out_host)
     return ALIFMM_OK;
 }
 
-extern "C" int alifmm_rays(alifmm_ctx *c, int32_t n_rays, const int32_t *src_iz, const int32_t *src_ix,
-                           const int32_t *rec_slot, int32_t cap, double *out_x, double *out_y, int32_t *out_len,
-                           double *out_time, int32_t *out_flag)
+// Validates the jobs, launches the ray kernel and leaves its outputs in the context's device buffers.
+static int rays_launch(alifmm_ctx *c, int32_t n_rays, const int32_t *src_iz, const int32_t *src_ix,
+                       const int32_t *rec_slot, int32_t cap, AliRayArgs &a)
 {
-    if (!c || !src_iz || !src_ix || !rec_slot || !out_len || !out_time)
-        return fail(ALIFMM_E_INVALID, "alifmm_rays: null argument");
     if (c->n_slots < 1) return fail(ALIFMM_E_STATE, "alifmm_rays: no resident travel-time fields (call alifmm_ttf first)");
     if (n_rays < 1) return fail(ALIFMM_E_INVALID, "alifmm_rays: n_rays must be >= 1");
     if (cap < 4) return fail(ALIFMM_E_INVALID, "alifmm_rays: capacity too small");
@@ -1092,7 +1159,6 @@ extern "C" int alifmm_rays(alifmm_ctx *c, int32_t n_rays, const int32_t *src_iz,
     if ((rc = dev_reserve(c->ray_time, (size_t)n_rays * sizeof(double))) != 0) return rc;
     if ((rc = dev_reserve(c->ray_len, (size_t)n_rays * sizeof(int))) != 0) return rc;
     if ((rc = dev_reserve(c->ray_flag, (size_t)n_rays * sizeof(int))) != 0) return rc;
-    AliRayArgs a;
     a.m = c->m; a.sg = c->sg; a.fz = c->fz; a.fx = c->fx;
     a.T = (const double *)c->T.p; a.rec = (const AliSourceRec *)c->rec.p; a.jobs = (const AliRayJob *)c->jobs.p;
     a.n_rays = n_rays; a.cap = cap;
@@ -1102,6 +1168,7 @@ extern "C" int alifmm_rays(alifmm_ctx *c, int32_t n_rays, const int32_t *src_iz,
     if (a.maxc < 32) a.maxc = 32;
     cudaStream_t s = c->stream;
     CUDA_TRY(cudaMemcpyAsync(c->jobs.p, jobs.data(), jobs.size() * sizeof(AliRayJob), cudaMemcpyHostToDevice, s));
+    // (pageable source: the call returns once `jobs` has been staged)
     const size_t smem = (size_t)ALI_RAY_WARPS * 3 * a.maxc * sizeof(double);
     if (smem > 48 * 1024) {
         if (smem > 200 * 1024) return fail(ALIFMM_E_INVALID, "alifmm_rays: subgrid too large for the ray kernel's shared memory");
@@ -1111,19 +1178,128 @@ extern "C" int alifmm_rays(alifmm_ctx *c, int32_t n_rays, const int32_t *src_iz,
     ali_rays_kernel<<<(n_rays + ALI_RAY_WARPS - 1) / ALI_RAY_WARPS, 32 * ALI_RAY_WARPS, smem, s>>>(a);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(c->ev[4], s));
-    CUDA_TRY(cudaMemcpyAsync(out_len, a.out_len, (size_t)n_rays * sizeof(int), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(out_time, a.out_time, (size_t)n_rays * sizeof(double), cudaMemcpyDeviceToHost, s));
-    if (out_flag) CUDA_TRY(cudaMemcpyAsync(out_flag, a.out_flag, (size_t)n_rays * sizeof(int), cudaMemcpyDeviceToHost, s));
-    if (out_x) CUDA_TRY(cudaMemcpyAsync(out_x, a.out_x, (size_t)n_rays * cap * sizeof(double), cudaMemcpyDeviceToHost, s));
-    if (out_y) CUDA_TRY(cudaMemcpyAsync(out_y, a.out_y, (size_t)n_rays * cap * sizeof(double), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
+    return ALIFMM_OK;
+}
+
+static void rays_counters(alifmm_ctx *c, int32_t n_rays, const int32_t *out_len, int launches)
+{
     float ms = 0;
     cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]);
     c->cnt.ms_rays = ms;
     c->cnt.rays = n_rays;
     c->cnt.ray_points = 0;
     for (int r = 0; r < n_rays; r++) c->cnt.ray_points += out_len[r];
-    c->cnt.kernel_launches = 1;
+    c->cnt.kernel_launches = launches;
+}
+
+extern "C" int alifmm_rays(alifmm_ctx *c, int32_t n_rays, const int32_t *src_iz, const int32_t *src_ix,
+                           const int32_t *rec_slot, int32_t cap, double *out_x, double *out_y, int32_t *out_len,
+                           double *out_time, int32_t *out_flag)
+{
+    if (!c || !src_iz || !src_ix || !rec_slot || !out_len || !out_time)
+        return fail(ALIFMM_E_INVALID, "alifmm_rays: null argument");
+    AliRayArgs a;
+    int rc = rays_launch(c, n_rays, src_iz, src_ix, rec_slot, cap, a);
+    if (rc != ALIFMM_OK) return rc;
+    cudaStream_t s = c->stream;
+    CUDA_TRY(cudaMemcpyAsync(out_len, a.out_len, (size_t)n_rays * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(out_time, a.out_time, (size_t)n_rays * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (out_flag) CUDA_TRY(cudaMemcpyAsync(out_flag, a.out_flag, (size_t)n_rays * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (out_x) CUDA_TRY(cudaMemcpyAsync(out_x, a.out_x, (size_t)n_rays * cap * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (out_y) CUDA_TRY(cudaMemcpyAsync(out_y, a.out_y, (size_t)n_rays * cap * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    rays_counters(c, n_rays, out_len, 1);
+    return ALIFMM_OK;
+}
+
+// Packs the used part of every ray (its first len[r] points, divided by `divisor`) back to back.
+__global__ void ali_ray_pack_kernel(const double *x, const double *y, const int *len, const long long *off, int cap,
+                                    double divisor, double *px, double *py)
+{
+    const int r = blockIdx.x;
+    const int n = len[r];
+    const double *sx = x + (size_t)r * cap, *sy = y + (size_t)r * cap;
+    double *dx = px + off[r], *dy = py + off[r];
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        dx[k] = sx[k] / divisor;
+        dy[k] = sy[k] / divisor;
+    }
+}
+
+// Pinned staging buffers are recycled like the device buffers (cudaHostAlloc costs tens of ms).
+static std::vector<PoolEntry> g_pin_pool;
+static void *pin_take(size_t bytes, size_t *got)
+{
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mutex);
+        for (size_t i = 0; i < g_pin_pool.size(); i++)
+            if (g_pin_pool[i].bytes >= bytes) {
+                void *p = g_pin_pool[i].p;
+                *got = g_pin_pool[i].bytes;
+                g_pin_pool[i] = g_pin_pool.back();
+                g_pin_pool.pop_back();
+                return p;
+            }
+    }
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    *got = bytes;
+    return p;
+}
+static void pin_give(void *p, size_t bytes)
+{
+    std::lock_guard<std::mutex> lk(g_pool_mutex);
+    g_pin_pool.push_back(PoolEntry{p, bytes, -1});
+}
+
+extern "C" int alifmm_rays_into(alifmm_ctx *c, int32_t n_rays, const int32_t *src_iz, const int32_t *src_ix,
+                                const int32_t *rec_slot, int32_t cap, double divisor, const int64_t *row, double *base_x,
+                                double *base_y, int32_t *out_len, double *out_time, int32_t *out_flag)
+{
+    if (!c || !src_iz || !src_ix || !rec_slot || !out_len || !out_time || !row || !base_x || !base_y)
+        return fail(ALIFMM_E_INVALID, "alifmm_rays_into: null argument");
+    if (!(divisor > 0)) return fail(ALIFMM_E_INVALID, "alifmm_rays_into: divisor must be positive");
+    for (int r = 0; r < n_rays; r++)
+        if (row[r] < 0) return fail(ALIFMM_E_INVALID, "alifmm_rays_into: negative row");
+    AliRayArgs a;
+    int rc = rays_launch(c, n_rays, src_iz, src_ix, rec_slot, cap, a);
+    if (rc != ALIFMM_OK) return rc;
+    cudaStream_t s = c->stream;
+    CUDA_TRY(cudaMemcpyAsync(out_len, a.out_len, (size_t)n_rays * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(out_time, a.out_time, (size_t)n_rays * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (out_flag) CUDA_TRY(cudaMemcpyAsync(out_flag, a.out_flag, (size_t)n_rays * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    std::vector<long long> off(n_rays + 1);
+    off[0] = 0;
+    for (int r = 0; r < n_rays; r++) {
+        if (out_len[r] < 0 || out_len[r] > cap) return fail(ALIFMM_E_STATE, "alifmm_rays_into: ray length out of range");
+        off[r + 1] = off[r] + out_len[r];
+    }
+    const size_t total = (size_t)off[n_rays];
+    if (total > 0) {
+        if ((rc = dev_reserve(c->ray_off, (size_t)(n_rays + 1) * sizeof(long long))) != 0) return rc;
+        if ((rc = dev_reserve(c->pack, 2 * total * sizeof(double))) != 0) return rc;
+        double *px = (double *)c->pack.p, *py = px + total;
+        CUDA_TRY(cudaMemcpyAsync(c->ray_off.p, off.data(), off.size() * sizeof(long long), cudaMemcpyHostToDevice, s));
+        ali_ray_pack_kernel<<<n_rays, 128, 0, s>>>(a.out_x, a.out_y, a.out_len, (const long long *)c->ray_off.p, cap, divisor, px, py);
+        CUDA_TRY(cudaGetLastError());
+        size_t pin_bytes = 0;
+        double *pin = (double *)pin_take(2 * total * sizeof(double), &pin_bytes);
+        if (!pin) return fail(ALIFMM_E_CUDA, "alifmm_rays_into: cannot allocate the pinned staging buffer");
+        cudaError_t e = cudaMemcpyAsync(pin, px, 2 * total * sizeof(double), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) {
+            pin_give(pin, pin_bytes);
+            return fail(ALIFMM_E_CUDA, std::string("alifmm_rays_into: ") + cudaGetErrorString(e));
+        }
+        for (int r = 0; r < n_rays; r++) {
+            const size_t n = (size_t)out_len[r];
+            memcpy(base_x + (size_t)row[r] * cap, pin + off[r], n * sizeof(double));
+            memcpy(base_y + (size_t)row[r] * cap, pin + total + off[r], n * sizeof(double));
+        }
+        pin_give(pin, pin_bytes);
+    }
+    rays_counters(c, n_rays, out_len, total > 0 ? 2 : 1);
     return ALIFMM_OK;
 }
 
@@ -1133,8 +1309,17 @@ extern "C" int alifmm_mem_info(alifmm_ctx *c, int64_t *free_bytes, int64_t *tota
     CUDA_TRY(cudaSetDevice(c->device));
     size_t f = 0, t = 0;
     CUDA_TRY(cudaMemGetInfo(&f, &t));
-    if (free_bytes) *free_bytes = (int64_t)f;
+    if (free_bytes) *free_bytes = (int64_t)(f + pool_bytes(c->device));   // pooled buffers are reusable
     if (total_bytes) *total_bytes = (int64_t)t;
+    return ALIFMM_OK;
+}
+
+extern "C" int alifmm_trim(int device)
+{
+    pool_trim(device);
+    std::lock_guard<std::mutex> lk(g_pool_mutex);
+    for (PoolEntry &e : g_pin_pool) cudaFreeHost(e.p);
+    g_pin_pool.clear();
     return ALIFMM_OK;
 }
 

@@ -120,7 +120,21 @@ int alifmm_rays(alifmm_ctx *ctx, int32_t n_rays, const int32_t *src_iz, const in
                 const int32_t *rec_slot, int32_t capacity, double *out_x, double *out_y, int32_t *out_len,
                 double *out_time, int32_t *out_flag);
 
-/* Free / total bytes of the context's device (used by the host side to size batches). */
+/* Same rays, delivered in the reference's dense layout (ALI_FMM.ray_paths_x / ray_paths_y,
+ * ATR:4306-4307): ray r is written to base_x + row[r] * capacity (its first out_len[r] points,
+ * each divided by `divisor` -- the reference's callers divide the fine-grid coordinates by
+ * subgrid_size, ATR:3729-3730, 4355-4356); the rest of the row is left untouched.  Only the used
+ * points cross PCIe (packed on the device, one copy through a pinned staging buffer). */
+int alifmm_rays_into(alifmm_ctx *ctx, int32_t n_rays, const int32_t *src_iz, const int32_t *src_ix,
+                     const int32_t *rec_slot, int32_t capacity, double divisor, const int64_t *row, double *base_x,
+                     double *base_y, int32_t *out_len, double *out_time, int32_t *out_flag);
+
+/* Device and pinned buffers of destroyed contexts are kept for the next context of the same
+ * process (ALI_FMM creates one per call).  alifmm_trim(device) releases them (device < 0: all). */
+int alifmm_trim(int device);
+
+/* Free / total bytes of the context's device (used by the host side to size batches); buffers held
+ * for reuse count as free. */
 int alifmm_mem_info(alifmm_ctx *ctx, int64_t *free_bytes, int64_t *total_bytes);
 
 /* Work counters and device timings of the last calls (feeds bench.py's roofline). */

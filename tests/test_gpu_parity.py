@@ -284,6 +284,34 @@ def test_rays_through_same_field_match_oracle(capi, orc):
     ctx.close()
 
 
+def test_rays_into_dense_layout_equals_plain_rays(capi):
+    """alifmm_rays_into (paths packed on the device, scattered into the reference's dense
+    [n, n, 5(nz+nx)] arrays, coordinates divided by subgrid_size) == alifmm_rays / subgrid_size."""
+    c = models.weld_crop(60, 80)
+    ctx = _ctx(capi, c)
+    sg = 3
+    ctx.ttf(np.array([59, 0], dtype=np.int32), np.array([70, 5], dtype=np.int32), sg, fetch=False)
+    srcs = [(0, 10), (0, 40), (30, 0), (0, 79), (59, 0), (20, 35)]
+    siz, six = [s[0] for s in srcs], [s[1] for s in srcs]
+    slots = [0, 1, 0, 1, 1, 0]
+    cap = 5 * (60 + 80)
+    x, y, ln, tm, fl = ctx.rays(siz, six, slots, cap)
+    bx, by = np.full((4, 5, cap), -7.0), np.full((4, 5, cap), -7.0)
+    rows = np.array([3, 19, 0, 7, 12, 8])
+    ln2, tm2, fl2 = ctx.rays_into(siz, six, slots, cap, sg, rows, bx, by)
+    assert np.array_equal(ln, ln2) and np.array_equal(tm, tm2) and np.array_equal(fl, fl2)
+    fx, fy = bx.reshape(20, cap), by.reshape(20, cap)
+    for r, row in enumerate(rows):
+        assert np.array_equal(fx[row, :ln[r]], x[r, :ln[r]] / sg) and np.array_equal(fy[row, :ln[r]], y[r, :ln[r]] / sg)
+        assert (fx[row, ln[r]:] == -7.0).all()            # the rest of the row is left untouched
+    untouched = np.setdiff1d(np.arange(20), rows)
+    assert (fx[untouched] == -7.0).all() and (fy[untouched] == -7.0).all()
+    with pytest.raises(ValueError):
+        ctx.rays_into(siz, six, slots, cap, sg, rows + 20, bx, by)
+    ctx.close()
+    capi.trim()
+
+
 def test_weld_sg9_rays_against_reference(capi):
     """Headline-size end to end: field + rays of receiver 40 on the GPU against the reference's
     ray paths and times (Weld_rays.py geometry)."""
