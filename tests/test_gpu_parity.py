@@ -140,6 +140,131 @@ def test_edge_and_corner_sources(capi, orc):
     ctx.close()
 
 
+# ----------------------------------------------------------------------------- BASELINE configs 3, 4, 5
+def test_voronoi_config4_fields_match_oracle(capi, orc):
+    """BASELINE config 4 at a size the oracle finishes in seconds: randomly oriented Voronoi grains
+    (Christoffel steel), sources on the lattice, travel() (subgrid 1), one batch."""
+    n = 768
+    m = models.voronoi(n, n * n // 4096, 1234)
+    scx, scz = models.lattice_sources(n, m["dnx"], rows=4, cols=2)
+    iz, ix = _nodes(m, scx, scz)
+    ctx = _ctx(capi, m)
+    T = ctx.ttf(iz, ix, 1)
+    om = _omodel(orc, m)
+    from tests.emu import emu
+    for k in range(len(iz)):
+        ref = orc.travel(om, scx[k], scz[k], m["dnx"])
+        # 0-2 % of the nodes (depending on the source; measured 0.9800 ... 1.0000 within 1e-5) sit behind a heap glitch of the reference (DESIGN.md 3,
+        # tests/test_kernel_replay.py::test_replay_deviations_start_at_reference_glitches) ...
+        _check_field(ref, T[k], frac=0.97, med=1e-7, worst=5e-3, what=("voronoi", k))
+        if k in (0, 5):
+            # ... and the kernel agrees with the host replay of its algorithm to rounding level, except
+            # behind the rare node where one ulp of atan/sin/cos decides between two stencils (source 5:
+            # 0.9 % of the nodes; the replay with injected ulp noise shows the same effect,
+            # tests/test_kernel_replay.py::test_replay_last_ulp_sensitivity*)
+            R, _, rc = emu.ttf(om, m["dnx"], int(iz[k]), int(ix[k]), 1)
+            d = models.rel_err(R, T[k])
+            assert rc == 0 and (d <= 1e-5).mean() >= 0.98 and np.median(d) <= 1e-12 and d.max() <= 5e-3
+    ctx.close()
+
+
+def test_voronoi_config4_full_size(capi, orc):
+    """BASELINE config 4 at full size (4096 x 4096, 4096 grains): four of the 128 lattice sources in
+    one batch; one field against the oracle, the others through size-independent properties (a
+    source solved alone gives the same bits; the field is a causal fixed point of the operator)."""
+    n = 4096
+    m = models.voronoi(n, 4096, 1234)
+    scx, scz = models.lattice_sources(n, m["dnx"])
+    sel = [0, 37, 90, 127]
+    iz, ix = _nodes(m, scx[sel], scz[sel])
+    ctx = _ctx(capi, m)
+    T = ctx.ttf(iz, ix, 1)
+    assert T.shape == (4, n, n) and np.isfinite(T).all() and (T >= 0).all()
+    c = ctx.counters()
+    assert c["node_solves"] == 4 * n * n
+    om = _omodel(orc, m)
+    ref = orc.travel(om, scx[sel[1]], scz[sel[1]], m["dnx"])
+    _check_field(ref, T[1], frac=0.99, med=1e-10, worst=5e-3, what="voronoi 4096")
+    alone = ctx.ttf(iz[2:3], ix[2:3], 1)[0]
+    assert np.array_equal(alone, T[2])
+    rng = np.random.default_rng(5)
+    ok = tot = 0
+    F = T[3]
+    for _ in range(300):
+        z, x = int(rng.integers(2, n - 2)), int(rng.integers(2, n - 2))
+        if max(abs(z - iz[3]), abs(x - ix[3])) < 48:
+            continue
+        z0, x0 = z - 2, x - 2                          # the operator only looks at the 5 x 5 window
+        win = np.ascontiguousarray(F[z0:z0 + 5, x0:x0 + 5])
+        sub = dict(veln=m["veln"][z0:z0 + 5, x0:x0 + 5], velpn=m["velpn"][z0:z0 + 5, x0:x0 + 5],
+                   vel_map=m["vel_map"][z0:z0 + 5, x0:x0 + 5], stif_den=m["stif_den"][z0:z0 + 5, x0:x0 + 5])
+        osub = _omodel(orc, {k: np.ascontiguousarray(v) for k, v in sub.items()})
+        nsts = np.where(win < win[2, 2], 0, -1).astype(np.int32)
+        v, _ = orc.update_node(osub, win, nsts, 2, 2, m["dnx"])
+        tot += 1
+        ok += abs(v - win[2, 2]) <= 1e-9 * win[2, 2]
+    assert tot > 200 and ok / tot >= 0.97, (ok, tot)
+    ctx.close()
+
+
+def test_long_grid_config5_proxy(capi, orc):
+    """Config 5's extent on one axis (16384 nodes) on a strip the oracle can solve: exercises the
+    packed 16-bit coordinates and the band capacity on a long front."""
+    nz, nx = 16384, 192
+    rng = np.random.default_rng(11)
+    veln = np.repeat(np.repeat(rng.uniform(0, 180, (nz // 64, nx // 64)), 64, axis=0), 64, axis=1)
+    m = dict(veln=veln, velpn=np.zeros((nz, nx), dtype=int), vel_map=np.ones((nz, nx)),
+             stif_den=models.const_stif((nz, nx)), dnx=1e-4)
+    ctx = _ctx(capi, m)
+    T = ctx.ttf(np.array([8192], dtype=np.int32), np.array([96], dtype=np.int32), 1)[0]
+    om = _omodel(orc, m)
+    ref = orc.travel(om, m["dnx"] * 96, m["dnx"] * 8192, m["dnx"])
+    e = models.rel_err(ref, T)
+    # a long channel carries every reference heap glitch to its end: 26 % of the nodes end up
+    # 1.1e-5 ... 2e-5 from the reference, none beyond 2.4e-3 (see the replay test named above) ...
+    assert (e <= 2e-5).mean() >= 0.9 and (e <= 1e-4).mean() >= 0.9999 and e.max() <= 5e-3 and np.median(e) <= 1e-8
+    # ... while the kernel and the host replay of its algorithm agree to rounding level
+    from tests.emu import emu
+    R, _, rc = emu.ttf(om, m["dnx"], 8192, 96, 1)
+    d = models.rel_err(R, T)                # (last-ulp libm differences can flip a stencil at isolated nodes)
+    assert rc == 0 and (d <= 1e-5).mean() >= 0.98 and np.median(d) <= 1e-12 and d.max() <= 5e-3
+    ctx.close()
+
+
+def test_fmc_config3_all_pairs(capi, orc):
+    """BASELINE config 3 in small: full-matrix capture on the weld (subgrid 3) -- every i != j
+    pair of 3 top + 3 bottom elements, including same-side pairs (rays along the surface), through
+    the class API; times and paths against the oracle's find_ray through the oracle's fields."""
+    from Anis_TTF_rays import ALI_FMM
+    w = models.weld()
+    dnx = w["dnx"]
+    xs = [33, 243, 467]
+    scx = np.array([dnx * x for x in xs] * 2)
+    scz = np.array([0.0] * 3 + [dnx * 423] * 3)
+    sg = 3
+    fm = ALI_FMM(w["veln"], w["velpn"], w["vel_map"], scx, scz, stif_den=w["stif_den"], dnx=dnx)
+    pairs = np.ones((6, 6)) - np.eye(6)
+    times = fm.find_all_TTF_rays(w["veln"], w["velpn"], w["vel_map"], subgrid_size=sg, trans_pairs=pairs,
+                                 stif_den=w["stif_den"])
+    assert (times > 0).sum() == 30 and not times.diagonal().any()
+    om = _omodel(orc, w)
+    good = 0
+    for j in range(6):
+        ref_T = orc.travel_finer_grid(om, scx[j], scz[j], dnx, sg)
+        for i in range(6):
+            if i == j:
+                continue
+            rx, ry, rt, _ = orc.find_ray(om, dnx, (sg * fm.isx[i], sg * fm.isz[i]), (sg * fm.isx[j], sg * fm.isz[j]), ref_T, sg)
+            x, y = fm.ray_path(i, j)
+            assert (x[0], y[0]) == (fm.isx[i], fm.isz[i]) and (x[-1], y[-1]) == (fm.isx[j], fm.isz[j])
+            same_path = models.polyline_distance(x, y, rx / sg, ry / sg) <= TOL_CELL
+            # a ray may settle on a neighbouring branch of nearly equal time where the two fields differ
+            # by a reference heap glitch (SURVEY.md 7.4; measured: 1 of the 30, 1.4 cells, 2.8e-4 in time)
+            assert abs(times[i, j] - rt) <= (1e-6 if same_path else 1e-3) * rt, (i, j, times[i, j], rt)
+            good += same_path
+    assert good >= 28, good
+
+
 # ----------------------------------------------------------------------------- fields, travel_finer_grid()
 @pytest.mark.parametrize("sg", [3, 5])
 def test_weld_crop_fine_fields_match_reference_golden(capi, sg):
