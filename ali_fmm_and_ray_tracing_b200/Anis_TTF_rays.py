@@ -93,7 +93,7 @@ class ALI_FMM:
     """Travel time fields and ray tracing in anisotropic media (reference: ATR:3789)."""
 
     # bytes of device memory one resident field node costs (T fp64 + status byte)
-    _BYTES_PER_NODE = 9
+    _BYTES_PER_NODE = 17   # result field f64 + tiled march field f64 + alive byte
     # fraction of the free device memory a batch of fields may take
     _MEM_FRACTION = 0.8
 

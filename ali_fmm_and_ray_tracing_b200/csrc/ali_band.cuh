@@ -36,18 +36,32 @@
 #define ALI_PACK_Z(p) ((int)((p) >> 16))
 #define ALI_PACK_X(p) ((int)((p) & 0xffffu))
 
+// Field layout.  The kernel marches on 4 x 4-node tiles (one 128-byte line per tile): a warp
+// works on 32 neighbouring front nodes, and on a row-major field every node of a steep front
+// segment sits in a line of its own, so each of the 12 gather instructions costs 32 L1 tag
+// look-ups -- the bound of phase A.  Tiles make that 8-9 for any front direction.  The host
+// replay keeps the row-major layout (t4x == 0); the finalize kernel writes the caller's
+// row-major field.
 struct AliBandGrid {
     int nz, nx;
-    double *T;        // [nz*nx] travel times of this source (seconds * sg on the fine path)
-    uint8_t *st;      // [nz*nx] ALI_ST_ALIVE once accepted
-    uint8_t *dirty;   // tiled [tiles_z][tiles_x][8][16]; 1: window changed since the node's last evaluation
+    double *T;        // travel times of this source (seconds * sg on the fine path), layout per t4x
+    uint8_t *st;      // same indexing; ALI_ST_ALIVE once accepted
+    uint8_t *dirty;   // host replay only: tiled [tiles_z][tiles_x][8][16]; 1: window changed since the last evaluation
     int tiles_x;
+    int t4x;          // 0: row-major [nz][nx]; else the number of 4-node tiles per row, (nx + 3) / 4
     AliMatView mv;
     double dnx;
-    ALI_DEV bool avail(int z, int x) const { return T[(size_t)z * nx + x] >= 0.0; } // false for NaN
-    ALI_DEV bool alive(int z, int x) const { return st[(size_t)z * nx + x] == ALI_ST_ALIVE; }
-    ALI_DEV double tt(int z, int x) const { return T[(size_t)z * nx + x]; }
+    ALI_DEV size_t ti(int z, int x) const
+    {
+        if (t4x) return ((((size_t)(z >> 2) * (size_t)t4x + (size_t)(x >> 2)) << 4) | (size_t)(((z & 3) << 2) | (x & 3)));
+        return (size_t)z * nx + x;
+    }
+    ALI_DEV bool avail(int z, int x) const { return T[ti(z, x)] >= 0.0; } // false for NaN
+    ALI_DEV bool alive(int z, int x) const { return st[ti(z, x)] == ALI_ST_ALIVE; }
+    ALI_DEV double tt(int z, int x) const { return T[ti(z, x)]; }
 };
+
+ALI_HD size_t ali_field_nodes_tiled(int nz, int nx) { return (size_t)((nz + 3) >> 2) * (size_t)((nx + 3) >> 2) * 16; }
 
 ALI_HD int ali_dirty_tiles_x(int nx) { return (nx + 15) >> 4; }
 ALI_HD size_t ali_dirty_bytes(int nz, int nx) { return (size_t)((nz + 7) >> 3) * (size_t)ali_dirty_tiles_x(nx) * 128; }
@@ -65,11 +79,24 @@ ALI_HD AliMatView ali_band_view(int sg)
 ALI_DEV void ali_band_gather(const AliBandGrid &g, int iz, int ix, AliWindow &w)
 {
     if (iz >= 2 && iz < g.nz - 2 && ix >= 2 && ix < g.nx - 2) {
-        const double *tp = g.T + ((size_t)iz * g.nx + ix);
-        const int nx = g.nx;
         unsigned av = 0;
+        if (g.t4x) {
+            // tiled address = row term + column term
+            unsigned rt[5], ct[5];
 #pragma unroll
-        for (int k = 0; k < 12; k++) w.t[k] = tp[ALI_W_DZ(k) * nx + ALI_W_DX(k)];
+            for (int q = 0; q < 5; q++) {
+                const int z = iz + q - 2, x = ix + q - 2;
+                rt[q] = (((unsigned)(z >> 2) * (unsigned)g.t4x) << 4) | (unsigned)((z & 3) << 2);
+                ct[q] = ((unsigned)(x >> 2) << 4) | (unsigned)(x & 3);
+            }
+#pragma unroll
+            for (int k = 0; k < 12; k++) w.t[k] = g.T[rt[ALI_W_DZ(k) + 2] + ct[ALI_W_DX(k) + 2]];
+        } else {
+            const double *tp = g.T + ((size_t)iz * g.nx + ix);
+            const int nx = g.nx;
+#pragma unroll
+            for (int k = 0; k < 12; k++) w.t[k] = tp[ALI_W_DZ(k) * nx + ALI_W_DX(k)];
+        }
 #pragma unroll
         for (int k = 0; k < 12; k++)
             if (w.t[k] >= 0.0) av |= 1u << k;
@@ -133,12 +160,12 @@ ALI_DEV void ali_band_mark_dirty(const AliBandGrid &g, int iz, int ix)
 // Phase B: make the staged value visible if it changed anything.
 ALI_DEV bool ali_band_changed(const AliBandGrid &g, int iz, int ix, double v)
 {
-    return !(g.T[(size_t)iz * g.nx + ix] == v);   // also true for a node without an estimate yet (NaN)
+    return !(g.T[g.ti(iz, ix)] == v);   // also true for a node without an estimate yet (NaN)
 }
 
 ALI_DEV void ali_band_store(const AliBandGrid &g, int iz, int ix, double v)
 {
-    g.T[(size_t)iz * g.nx + ix] = v;
+    g.T[g.ti(iz, ix)] = v;
     ali_band_mark_dirty(g, iz, ix);
 }
 
@@ -166,29 +193,30 @@ ALI_DEV bool ali_band_claim(const AliBandGrid &g, size_t node)
 // common snapshot).  Returns the packed new entries.
 ALI_DEV int ali_band_accept(const AliBandGrid &g, int iz, int ix, unsigned *nb)
 {
-    const size_t node = (size_t)iz * g.nx + ix;
     int cnt = 0;
-    g.st[node] = ALI_ST_ALIVE;
+    g.st[g.ti(iz, ix)] = ALI_ST_ALIVE;
+    const bool hw = ix > 0, he = ix < g.nx - 1, hn = iz > 0, hs = iz < g.nz - 1;
+    const size_t nw = hw ? g.ti(iz, ix - 1) : 0, ne = he ? g.ti(iz, ix + 1) : 0;
+    const size_t nn = hn ? g.ti(iz - 1, ix) : 0, ns = hs ? g.ti(iz + 1, ix) : 0;
 #if defined(__CUDA_ARCH__)
     // the four state words are loaded together (one memory latency), then only far ones are claimed
-    const bool hw = ix > 0, he = ix < g.nx - 1, hn = iz > 0, hs = iz < g.nz - 1;
-    const volatile unsigned long long *tw = (const volatile unsigned long long *)(g.T + node);
-    const unsigned long long vw = hw ? tw[-1] : 0ull, ve = he ? tw[1] : 0ull;
-    const unsigned long long vn = hn ? tw[-(long long)g.nx] : 0ull, vs = hs ? tw[g.nx] : 0ull;
-    unsigned long long *cw = (unsigned long long *)(g.T + node);
-    if (vw == ALI_T_FAR_BITS && atomicCAS(cw - 1, ALI_T_FAR_BITS, ALI_T_ENLISTED_BITS) == ALI_T_FAR_BITS)
+    const volatile unsigned long long *tw = (const volatile unsigned long long *)g.T;
+    const unsigned long long vw = hw ? tw[nw] : 0ull, ve = he ? tw[ne] : 0ull;
+    const unsigned long long vn = hn ? tw[nn] : 0ull, vs = hs ? tw[ns] : 0ull;
+    unsigned long long *cw = (unsigned long long *)g.T;
+    if (vw == ALI_T_FAR_BITS && atomicCAS(cw + nw, ALI_T_FAR_BITS, ALI_T_ENLISTED_BITS) == ALI_T_FAR_BITS)
         nb[cnt++] = ALI_PACK(iz, ix - 1);
-    if (ve == ALI_T_FAR_BITS && atomicCAS(cw + 1, ALI_T_FAR_BITS, ALI_T_ENLISTED_BITS) == ALI_T_FAR_BITS)
+    if (ve == ALI_T_FAR_BITS && atomicCAS(cw + ne, ALI_T_FAR_BITS, ALI_T_ENLISTED_BITS) == ALI_T_FAR_BITS)
         nb[cnt++] = ALI_PACK(iz, ix + 1);
-    if (vn == ALI_T_FAR_BITS && atomicCAS(cw - g.nx, ALI_T_FAR_BITS, ALI_T_ENLISTED_BITS) == ALI_T_FAR_BITS)
+    if (vn == ALI_T_FAR_BITS && atomicCAS(cw + nn, ALI_T_FAR_BITS, ALI_T_ENLISTED_BITS) == ALI_T_FAR_BITS)
         nb[cnt++] = ALI_PACK(iz - 1, ix);
-    if (vs == ALI_T_FAR_BITS && atomicCAS(cw + g.nx, ALI_T_FAR_BITS, ALI_T_ENLISTED_BITS) == ALI_T_FAR_BITS)
+    if (vs == ALI_T_FAR_BITS && atomicCAS(cw + ns, ALI_T_FAR_BITS, ALI_T_ENLISTED_BITS) == ALI_T_FAR_BITS)
         nb[cnt++] = ALI_PACK(iz + 1, ix);
 #else
-    if (ix > 0 && ali_band_claim(g, node - 1)) nb[cnt++] = ALI_PACK(iz, ix - 1);
-    if (ix < g.nx - 1 && ali_band_claim(g, node + 1)) nb[cnt++] = ALI_PACK(iz, ix + 1);
-    if (iz > 0 && ali_band_claim(g, node - g.nx)) nb[cnt++] = ALI_PACK(iz - 1, ix);
-    if (iz < g.nz - 1 && ali_band_claim(g, node + g.nx)) nb[cnt++] = ALI_PACK(iz + 1, ix);
+    if (hw && ali_band_claim(g, nw)) nb[cnt++] = ALI_PACK(iz, ix - 1);
+    if (he && ali_band_claim(g, ne)) nb[cnt++] = ALI_PACK(iz, ix + 1);
+    if (hn && ali_band_claim(g, nn)) nb[cnt++] = ALI_PACK(iz - 1, ix);
+    if (hs && ali_band_claim(g, ns)) nb[cnt++] = ALI_PACK(iz + 1, ix);
 #endif
     return cnt;
 }

@@ -31,8 +31,8 @@ struct alignas(8) AliHeapEnt {
 
 struct AliSeqGrid {
     int nz, nx;           // full extents of this grid (edge logic, absolute coordinates)
-    double *t;            // T(z, x) = t[z * t_stride + x]
-    long long t_stride;
+    double *t;            // T(z, x) = t[z * t_stride + x - toff]: a buffer of the status window's extent
+    long long t_stride, toff;
     int32_t *st;
     int wz0, wx0, wnz, wnx;
     AliHeapEnt *heap;     // 1-indexed (ATR:118-119): packed node + its window index
@@ -53,17 +53,13 @@ struct AliSeqGrid {
     ALI_DEV size_t widx(int z, int x) const { return (size_t)(z - wz0) * wnx + (x - wx0); }
     ALI_DEV int32_t &s(int z, int x) const { return st[(size_t)(z - wz0) * wnx + (x - wx0)]; }
     ALI_DEV int32_t status(int z, int x) const { return in_win(z, x) ? s(z, x) : -1; }
-    // A node has an estimate (reference: nsts >= 0) exactly when its T is not NaN: level grids are
-    // reset to NaN, the main field is pre-filled with NaN, values are only ever written together with
-    // a status >= 0.  Outside the status window the main field is NaN.  The grid test stays: level 1 of
-    // travel() asks with a wrong nnz (ATR:1645) and would read past the level otherwise.
-    ALI_DEV bool avail(int z, int x) const
-    {
-        return z >= 0 && z < nz && x >= 0 && x < nx && t[(long long)z * t_stride + x] >= 0.0;
-    }
+    // A node has an estimate (reference: nsts >= 0) exactly when its T is not NaN: the buffers are
+    // reset to NaN and values are only ever written together with a status >= 0.  Outside the window
+    // (also when level 1 of travel() asks with a wrong nnz, ATR:1645) there is no estimate.
+    ALI_DEV bool avail(int z, int x) const { return in_win(z, x) && t[(long long)z * t_stride + x - toff] >= 0.0; }
     ALI_DEV bool alive(int z, int x) const { return in_win(z, x) && s(z, x) == 0; }
-    ALI_DEV double &tref(int z, int x) const { return t[(long long)z * t_stride + x]; }
-    ALI_DEV double tt(int z, int x) const { return t[(long long)z * t_stride + x]; }
+    ALI_DEV double &tref(int z, int x) const { return t[(long long)z * t_stride + x - toff]; }
+    ALI_DEV double tt(int z, int x) const { return t[(long long)z * t_stride + x - toff]; }
 };
 
 // Python round(k / 2): round-half-to-even (ATR:123, 135, 160, 172).
@@ -196,6 +192,35 @@ ALI_DEV void ali_downtree(AliSeqGrid &g)
     g.ntr = ntr;
 }
 
+// One evaluation of a node of a sequential grid (ali_eval_node with a branch-free gather for nodes
+// two or more inside the status window, where every window node is inside the grid as well).
+ALI_DEV double ali_seq_eval(const AliModel &m, const AliSeqGrid &g, int iz, int ix, int nnz_logic, int *used_fallback)
+{
+    if (nnz_logic == g.nz && iz - 2 >= g.wz0 && iz + 2 < g.wz0 + g.wnz && ix - 2 >= g.wx0 && ix + 2 < g.wx0 + g.wnx) {
+        AliMat mat;
+        AliWindow w;
+        ali_fetch_mat(m, g.mv, iz, ix, mat);
+        const double *tp = g.t + ((long long)iz * g.t_stride + ix - g.toff);
+        const long long st = g.t_stride;
+        unsigned av = 0;
+#pragma unroll
+        for (int k = 0; k < 12; k++) w.t[k] = tp[ALI_W_DZ(k) * st + ALI_W_DX(k)];
+#pragma unroll
+        for (int k = 0; k < 12; k++) {
+            if (w.t[k] >= 0.0) av |= 1u << k;
+            else w.t[k] = 0.0;   // as ali_gather leaves it
+        }
+        w.avail = av;
+        double v = ali_update_window(m, mat, w, iz, ix, g.nz, g.nx, g.dnx, nullptr);
+        if (v == -1.0) {
+            v = ali_fouds18(m, mat, g, iz, ix, g.dnx, g.dnx, g.nx, g.nz);
+            if (used_fallback) *used_fallback = 1;
+        }
+        return v;
+    }
+    return ali_eval_node(m, g.mv, g, iz, ix, nnz_logic, g.nx, g.nz, g.nx, g.dnx, used_fallback);
+}
+
 struct AliSeqCounters {
     long long pops, evals, fallbacks;
     long long cyc_heap, cyc_eval;   // device builds: SM cycles in heap operations / evaluations
@@ -246,7 +271,7 @@ ALI_DEV int ali_seq_march(AliSeqGrid &g, const AliModel &m, int cx, int cz, int 
                     int nnz_l = (nnz_bug && s < 2 && stv > 0) ? nnx : nnz;
                     int fb = 0;
                     long long c1 = ALI_CLOCK();
-                    double v = ali_eval_node(m, g.mv, g, z, x, nnz_l, nnx, nnz, nnx, g.dnx, &fb);
+                    double v = ali_seq_eval(m, g, z, x, nnz_l, &fb);
                     long long c2 = ALI_CLOCK();
                     cnt.evals++;
                     cnt.fallbacks += fb;
@@ -352,7 +377,7 @@ ALI_DEV bool ali_coop_wanted_node(const AliSeqGrid &g, int cz, int cx)
 ALI_DEV int ali_coop_step(const AliSeqGrid &g, const AliModel &m, AliCoopState &cs, bool serve, bool has_cand, int cz,
                           int cx)
 {
-    const int nnx = g.nx, nnz = g.nz;
+    const int nnz = g.nz;
     int cnnz = nnz;
     if (serve) {
         cz = cs.mz; cx = cs.mx; cnnz = cs.mnnz;
@@ -360,7 +385,7 @@ ALI_DEV int ali_coop_step(const AliSeqGrid &g, const AliModel &m, AliCoopState &
         return 0;
     }
     int fb = 0;
-    const double v = ali_eval_node(m, g.mv, g, cz, cx, cnnz, nnx, nnz, nnx, g.dnx, &fb);
+    const double v = ali_seq_eval(m, g, cz, cx, cnnz, &fb);
     if (serve) {
         cs.miss_v = v; cs.miss_fb = fb; cs.miss_ready = 1; cs.miss = 0;
     } else if (!fb) {
@@ -735,7 +760,7 @@ ALI_DEV void ali_src_level_geometry(AliSrcState &s, const AliModel &m, const Ali
     g.nx = scl * (right - left) + 1;
     g.t = cur == 0 ? sc.tA : sc.tB;
     g.st = cur == 0 ? sc.sA : sc.sB;
-    g.t_stride = g.nx;
+    g.t_stride = g.nx; g.toff = 0;
     g.wz0 = 0; g.wx0 = 0; g.wnz = g.nz; g.wnx = g.nx;
     g.heap = sc.heap; g.heap_cap = sc.heap_cap; g.hkey = sc.hkey;
     g.cv = sc.cval; g.cf = sc.cflag;
@@ -791,18 +816,21 @@ ALI_DEV int ali_src_level_seq_coop(AliSrcState &s, const AliModel &m, const AliS
     return why;
 }
 
-ALI_DEV void ali_src_main_geometry(AliSrcState &s, const AliModel &m, const AliSourcePlan &p, const AliSeqScratch &sc,
-                                   double *T)
+// Main grid: statuses and travel times of a window around the source, in the level buffers that
+// the last level does not use.  The band march copies the window into its own field afterwards.
+ALI_DEV void ali_src_main_geometry(AliSrcState &s, const AliModel &m, const AliSourcePlan &p, const AliSeqScratch &sc)
 {
     AliSeqGrid &mg = s.mg;
     const int last = (p.nlev - 1) & 1;
     const int half = p.stop_r + 4;
     mg.nz = p.nz; mg.nx = p.nx;
-    mg.t = T; mg.t_stride = p.nx;
     mg.st = last == 0 ? sc.sB : sc.sA;
+    mg.t = last == 0 ? sc.tB : sc.tA;
     mg.wz0 = ali_imax(0, p.isz - half); mg.wx0 = ali_imax(0, p.isx - half);
     mg.wnz = ali_imin(p.nz - 1, p.isz + half) - mg.wz0 + 1;
     mg.wnx = ali_imin(p.nx - 1, p.isx + half) - mg.wx0 + 1;
+    mg.t_stride = mg.wnx;
+    mg.toff = (long long)mg.wz0 * mg.wnx + mg.wx0;
     mg.heap = sc.heap; mg.heap_cap = sc.heap_cap; mg.hkey = sc.hkey;
     mg.cv = sc.cval; mg.cf = sc.cflag;
     mg.mv = s.base;
@@ -818,11 +846,11 @@ ALI_DEV void ali_src_main_start_and_seq(AliSrcState &s, const AliModel &m, const
     s.overflow |= s.mg.overflow;
 }
 
-// Levels + main-grid start for one source.  `T` is the source's main-grid field.  With an
+// Levels + main-grid start for one source (result: statuses + travel times of res' window).  With an
 // evaluation cache in the scratch (sc.cval) the marches run in their cooperative form, else lane
 // 0 alone walks them and the other lanes only take part in the fills.
-ALI_DEV void ali_seq_source(const AliModel &m, const AliSourcePlan &p, const AliSeqScratch &sc, double *T,
-                            AliSeqResult &res, int lane, int nlanes)
+ALI_DEV void ali_seq_source(const AliModel &m, const AliSourcePlan &p, const AliSeqScratch &sc, AliSeqResult &res,
+                            int lane, int nlanes)
 {
     AliSrcState s;
     const bool coop = sc.cval != nullptr;
@@ -837,12 +865,12 @@ ALI_DEV void ali_seq_source(const AliModel &m, const AliSourcePlan &p, const Ali
         else if (lane == 0) ali_src_level_seq(s, m, p, l, -1);
         ALI_SYNCWARP();
     }
-    ali_src_main_geometry(s, m, p, sc, T);
+    ali_src_main_geometry(s, m, p, sc);
 #if defined(__CUDA_ARCH__)
     s.overflow = __shfl_sync(0xffffffffu, s.overflow, 0);
 #endif
     if (!s.overflow) {
-        ali_seq_clear(s.mg, false, lane, nlanes);
+        ali_seq_clear(s.mg, true, lane, nlanes);
         ALI_SYNCWARP();
         const int last = (p.nlev - 1) & 1;
         if (lane == 0) ali_seq_handoff(s.lv[last], s.cz[last], s.cx[last], s.mg, p.isz, p.isx);

@@ -62,8 +62,10 @@ struct AliBatch {
     int nz, nx;             // extents of the solved grid
     int margin;
     double delta;
-    double *T;              // [n_src][nz*nx]
-    uint8_t *st;            // [n_src][nz*nx]
+    double *T;              // [n_src][nz*nx] result, row-major (written by the finalize kernel)
+    double *Tt;             // [n_src][tn] field the band march works on, 4 x 4-node tiles (ali_band.cuh)
+    uint8_t *st;            // [n_src][tn] alive flags, same indexing
+    size_t tn;              // ali_field_nodes_tiled(nz, nx)
     // sequential scratch, per source
     double *seq_t;          // [n_src][2*seq_cap]
     int32_t *seq_s;         // [n_src][2*seq_cap]
@@ -128,7 +130,7 @@ __global__ void __launch_bounds__(32, 1) ali_seq_kernel(AliBatch b)
     sc.heap_cap = b.heap_cap;
     sc.status_cap = b.seq_cap;
     AliSeqResult res;
-    ali_seq_source(b.m, p, sc, b.T + (size_t)src * b.nz * b.nx, res, lane, 32);
+    ali_seq_source(b.m, p, sc, res, lane, 32);
     if (lane == 0) {
         rec.seq = res;
         rec.overflow = res.overflow ? 1 : 0;
@@ -255,8 +257,9 @@ __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
 
     AliBandGrid g;
     g.nz = b.nz; g.nx = b.nx;
-    g.T = b.T + (size_t)src * b.nz * b.nx;
-    g.st = b.st + (size_t)src * b.nz * b.nx;
+    g.T = b.Tt + (size_t)src * b.tn;
+    g.st = b.st + (size_t)src * b.tn;
+    g.t4x = (b.nx + 3) >> 2;
     g.dirty = nullptr;   // window-changed marks live in shared memory here (s_dmap); the byte map is the host replay's
     g.tiles_x = 0;
     g.dnx = b.m.dnx;
@@ -285,28 +288,34 @@ __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
     __syncthreads();
     if (s_overflow) return;
 
-    // hand-over: window statuses of the sequential phase -> byte statuses + first band list;
-    // every band node starts dirty (in the work list)
+    // hand-over: window of the sequential phase (statuses + travel times in its level buffers) ->
+    // tiled field + alive flags + first band list; every band node starts in the work list
     {
         const AliSeqResult w = rec.seq;
         const int nlev = b.sg > 1 ? 2 : 3;
-        const int32_t *wst = b.seq_s + (size_t)src * 2 * b.seq_cap + ((((nlev - 1) & 1) == 0) ? b.seq_cap : 0);
+        const size_t woff = (size_t)src * 2 * b.seq_cap + ((((nlev - 1) & 1) == 0) ? b.seq_cap : 0);
+        const int32_t *wst = b.seq_s + woff;
+        const double *wt = b.seq_t + woff;
         const int wn = w.wnz * w.wnx;
         for (int base = 0; base < wn; base += NT) {
             int i = base + tid;
             int k = 0;
             unsigned entry = 0;
+            double tv = 0.0;
             if (i < wn) {
                 int z = i / w.wnx, x = i - z * w.wnx;
                 int32_t s = wst[i];
-                size_t node = (size_t)(w.wz0 + z) * b.nx + (w.wx0 + x);
-                if (s == 0) g.st[node] = ALI_ST_ALIVE;
-                else if (s > 0) { k = 1; entry = ALI_PACK(w.wz0 + z, w.wx0 + x); } // holds an estimate: not claimable
-                else g.T[node] = __longlong_as_double((long long)ALI_T_FAR_BITS); // far: the hand-off copied 0 here (ATR:2010)
+                if (s >= 0) {   // far nodes keep the field's pre-filled "far" word
+                    tv = wt[i];
+                    const size_t node = g.ti(w.wz0 + z, w.wx0 + x);
+                    g.T[node] = tv;
+                    if (s == 0) g.st[node] = ALI_ST_ALIVE;
+                    else { k = 1; entry = ALI_PACK(w.wz0 + z, w.wx0 + x); }
+                }
             }
             int pos = ali_warp_reserve(k, &s_count[0]);
             if (k) {
-                if (pos < cap) { ent0[pos] = entry; wrk0[pos] = (unsigned)pos; val0[pos] = g.T[(size_t)ALI_PACK_Z(entry) * b.nx + ALI_PACK_X(entry)]; }
+                if (pos < cap) { ent0[pos] = entry; wrk0[pos] = (unsigned)pos; val0[pos] = tv; }
                 else s_overflow = 2;
             }
         }
@@ -365,8 +374,8 @@ __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
         // A node the FD fallback evaluated also depends on alive flags: it is re-evaluated every
         // round (its own bit), like the reference re-evaluates it on every neighbouring pop.
         if (tid == 0) s_force[(rounds + 1) & 1] = 0;
-        if (pmask & 1) { g.T[(size_t)ALI_PACK_Z(pe0) * g.nx + ALI_PACK_X(pe0)] = pv0; ali_dmap_mark(s_dmap, ALI_PACK_Z(pe0), ALI_PACK_X(pe0)); }
-        if (pmask & 2) { g.T[(size_t)ALI_PACK_Z(pe1) * g.nx + ALI_PACK_X(pe1)] = pv1; ali_dmap_mark(s_dmap, ALI_PACK_Z(pe1), ALI_PACK_X(pe1)); }
+        if (pmask & 1) { g.T[g.ti(ALI_PACK_Z(pe0), ALI_PACK_X(pe0))] = pv0; ali_dmap_mark(s_dmap, ALI_PACK_Z(pe0), ALI_PACK_X(pe0)); }
+        if (pmask & 2) { g.T[g.ti(ALI_PACK_Z(pe1), ALI_PACK_X(pe1))] = pv1; ali_dmap_mark(s_dmap, ALI_PACK_Z(pe1), ALI_PACK_X(pe1)); }
         if (pmask & 4) ali_dmap_row(s_dmap, ALI_PACK_Z(pe0), ALI_PACK_X(pe0), 1u);
         if (pmask & 8) ali_dmap_row(s_dmap, ALI_PACK_Z(pe1), ALI_PACK_X(pe1), 1u);
         for (int q = tid + 2 * NT; q < nwork; q += NT) {
@@ -375,7 +384,7 @@ __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
             const double v = val[i];
             if (v < 0.0) {
                 val[i] = -v;
-                g.T[(size_t)ALI_PACK_Z(e) * g.nx + ALI_PACK_X(e)] = -v;
+                g.T[g.ti(ALI_PACK_Z(e), ALI_PACK_X(e))] = -v;
                 ali_dmap_mark(s_dmap, ALI_PACK_Z(e), ALI_PACK_X(e));
             }
         }
@@ -524,11 +533,17 @@ __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
     }
 }
 
-// T / subgrid (ATR:2832); nodes the march never reached keep the reference's 0.
-__global__ void ali_finalize_kernel(double *T, size_t n, int sg)
+// Tiled march field -> the caller's row-major field, T / subgrid (ATR:2832); nodes the march never
+// reached get the reference's 0.  A warp reads 8 sectors of 8 tiles and writes 256 contiguous bytes;
+// the other three rows of those tiles are read by the next rows' warps out of L2.
+__global__ void ali_finalize_kernel(const double *Tt, double *T, int n_src, int nz, int nx, size_t tn, int sg)
 {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        double v = T[i];
+    const size_t N = (size_t)nz * nx, total = (size_t)n_src * N;
+    const size_t t4x = (size_t)((nx + 3) >> 2);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t src = i / N, r = i - src * N;
+        const int z = (int)(r / nx), x = (int)(r - (size_t)z * nx);
+        const double v = Tt[src * tn + ((((size_t)(z >> 2) * t4x + (size_t)(x >> 2)) << 4) | (size_t)(((z & 3) << 2) | (x & 3)))];
         T[i] = (v >= 0.0) ? v / sg : 0.0;
     }
 }
@@ -721,7 +736,7 @@ struct alifmm_ctx {
     int band_smem_bytes = 0;   // measured on B200: L1 for the T / status gathers is worth more than smem lists
     // resident batch
     int n_slots = 0, sg = 0, fz = 0, fx = 0;
-    DevBuf T, st, seq_t, seq_s, seq_heap, seq_hkey, seq_cval, seq_cflag, lists, stage, rec, jobs, ray_x, ray_y, ray_time, ray_len, ray_flag, ray_off, pack, misc;
+    DevBuf T, Tt, st, seq_t, seq_s, seq_heap, seq_hkey, seq_cval, seq_cflag, lists, stage, rec, jobs, ray_x, ray_y, ray_time, ray_len, ray_flag, ray_off, pack, misc;
     alifmm_counters_t cnt{};
 };
 
@@ -836,7 +851,7 @@ extern "C" void alifmm_destroy(alifmm_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (void *p : c->model_allocs) cudaFree(p);
-    DevBuf *bufs[] = {&c->T, &c->st, &c->seq_t, &c->seq_s, &c->seq_heap, &c->seq_hkey, &c->seq_cval, &c->seq_cflag, &c->lists, &c->stage, &c->rec, &c->jobs,
+    DevBuf *bufs[] = {&c->T, &c->Tt, &c->st, &c->seq_t, &c->seq_s, &c->seq_heap, &c->seq_hkey, &c->seq_cval, &c->seq_cflag, &c->lists, &c->stage, &c->rec, &c->jobs,
                       &c->ray_x, &c->ray_y, &c->ray_time, &c->ray_len, &c->ray_flag, &c->ray_off, &c->pack, &c->misc};
     for (DevBuf *b : bufs) dev_release(*b, c->device);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
@@ -1016,8 +1031,10 @@ static int ttf_attempt(alifmm_ctx *c, int32_t n_src, const int32_t *src_iz, cons
     *band_overflow = 0;
     b.resort_every = c->resort_every;
     int rc;
+    b.tn = ali_field_nodes_tiled(fz, fx);
     if ((rc = dev_reserve(c->T, (size_t)n_src * N * sizeof(double))) != 0) return rc;
-    if ((rc = dev_reserve(c->st, (size_t)n_src * N + 16)) != 0) return rc;
+    if ((rc = dev_reserve(c->Tt, (size_t)n_src * b.tn * sizeof(double))) != 0) return rc;
+    if ((rc = dev_reserve(c->st, (size_t)n_src * b.tn + 16)) != 0) return rc;
     if ((rc = dev_reserve(c->seq_t, (size_t)n_src * 2 * b.seq_cap * sizeof(double))) != 0) return rc;
     if ((rc = dev_reserve(c->seq_s, (size_t)n_src * 2 * b.seq_cap * sizeof(int32_t))) != 0) return rc;
     if ((rc = dev_reserve(c->seq_heap, (size_t)n_src * 2 * b.heap_cap * sizeof(int32_t))) != 0) return rc;
@@ -1027,7 +1044,7 @@ static int ttf_attempt(alifmm_ctx *c, int32_t n_src, const int32_t *src_iz, cons
     if ((rc = dev_reserve(c->lists, (size_t)n_src * 4 * b.band_cap * sizeof(unsigned))) != 0) return rc;
     if ((rc = dev_reserve(c->stage, (size_t)n_src * 2 * b.band_cap * sizeof(double))) != 0) return rc;
     if ((rc = dev_reserve(c->rec, (size_t)n_src * sizeof(AliSourceRec))) != 0) return rc;
-    b.T = (double *)c->T.p; b.st = (uint8_t *)c->st.p;
+    b.T = (double *)c->T.p; b.Tt = (double *)c->Tt.p; b.st = (uint8_t *)c->st.p;
     b.seq_t = (double *)c->seq_t.p; b.seq_s = (int32_t *)c->seq_s.p; b.seq_heap = (int32_t *)c->seq_heap.p;
     b.seq_hkey = (double *)c->seq_hkey.p; b.seq_cval = (double *)c->seq_cval.p; b.seq_cflag = (uint8_t *)c->seq_cflag.p;
     b.lists = (unsigned *)c->lists.p; b.stage = (double *)c->stage.p; b.rec = (AliSourceRec *)c->rec.p;
@@ -1039,8 +1056,8 @@ static int ttf_attempt(alifmm_ctx *c, int32_t n_src, const int32_t *src_iz, cons
     cudaStream_t s = c->stream;
     CUDA_TRY(cudaMemcpyAsync(b.rec, recs.data(), recs.size() * sizeof(AliSourceRec), cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaEventRecord(c->ev[0], s));
-    CUDA_TRY(cudaMemsetAsync(b.T, ALI_T_UNSET_BYTE, (size_t)n_src * N * sizeof(double), s)); // NaN = no estimate
-    CUDA_TRY(cudaMemsetAsync(b.st, 0, (size_t)n_src * N, s));
+    CUDA_TRY(cudaMemsetAsync(b.Tt, ALI_T_UNSET_BYTE, (size_t)n_src * b.tn * sizeof(double), s)); // NaN = far
+    CUDA_TRY(cudaMemsetAsync(b.st, 0, (size_t)n_src * b.tn, s));
     ali_seq_kernel<<<n_src, 32, 0, s>>>(b);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(c->ev[1], s));
@@ -1067,7 +1084,7 @@ static int ttf_attempt(alifmm_ctx *c, int32_t n_src, const int32_t *src_iz, cons
         size_t total = (size_t)n_src * N;
         int blocks = (int)((total + 255) / 256);
         if (blocks > 148 * 16) blocks = 148 * 16;
-        ali_finalize_kernel<<<blocks, 256, 0, s>>>(b.T, total, sg);
+        ali_finalize_kernel<<<blocks, 256, 0, s>>>(b.Tt, b.T, n_src, fz, fx, b.tn, sg);
         CUDA_TRY(cudaGetLastError());
     }
     CUDA_TRY(cudaEventRecord(c->ev[3], s));

@@ -275,7 +275,10 @@ def run_gpu(args):
     cap = 5 * (w["veln"].shape[0] + w["veln"].shape[1])
     h2d = int(w["veln"].nbytes + w["veln"].size * 4 + w["vel_map"].nbytes + w["stif_den"].nbytes + 2 * g.nbytes
               + n_src * 8 + n_rays * 12)
-    d2h = int(n_rays * (2 * cap * 8 + 16) + n_src * 200)
+    # device -> host per step: the used points of every ray (x and y, packed on the device), their
+    # lengths / times / flags, and the per-source records
+    ray_points = int(fm.last_counters[0]["ray_points"])
+    d2h = int(ray_points * 16 + n_rays * 16 + n_src * 200)
     assert (times > 0).sum() == n_rays
 
     if rank == 0:

@@ -119,7 +119,7 @@ static void band_run(const AliModel &m, AliBandGrid &bg, std::vector<unsigned> &
         tnew.resize(list.size());
         for (size_t i = 0; i < list.size(); i++) {
             const int iz = ALI_PACK_Z(list[i]), ix = ALI_PACK_X(list[i]);
-            const size_t node = (size_t)iz * bg.nx + ix;
+            const size_t node = bg.ti(iz, ix);
             const size_t di = ali_dirty_index(bg, iz, ix);
             if (bg.dirty[di] || eager) {
                 int fb = 0;
@@ -170,7 +170,8 @@ static void seq_to_band(const AliSeqGrid &g, AliBandGrid &bg, std::vector<unsign
         for (int x = 0; x < g.wnx; x++) {
             int32_t s = g.st[(size_t)z * g.wnx + x];
             const int az = g.wz0 + z, ax = g.wx0 + x;
-            size_t node = (size_t)az * bg.nx + ax;
+            size_t node = bg.ti(az, ax);
+            if (s >= 0) bg.T[node] = g.tt(az, ax);   // the sequential phase keeps its window in its own buffer
             if (s == 0) bg.st[node] = ALI_ST_ALIVE;
             else if (s > 0) { list.push_back(ALI_PACK(az, ax)); bg.dirty[ali_dirty_index(bg, az, ax)] = 1; }
             else { unsigned long long bits = ALI_T_FAR_BITS; std::memcpy(&bg.T[node], &bits, 8); }
@@ -194,6 +195,8 @@ static void band_to_seq(const AliBandGrid &bg, AliSeqGrid &g)
 //           [9] level band evals, [10] cooperative steps, [11] evaluations executed in them
 // Lanes of the cooperative sequential march (ali_seq.cuh); 0 = lane 0 alone walks the reference's loop.
 static int g_coop_lanes = 32;
+static int g_tiled = 0;   // replay the band march on the kernel's 4 x 4-tiled field layout
+extern "C" void emu_set_tiled(int on) { g_tiled = on; }
 extern "C" void emu_set_coop(int nlanes) { g_coop_lanes = nlanes; }
 
 extern "C" int emu_ttf(int nz, int nx, const double *veln, const int32_t *velpn, const double *vel_map,
@@ -243,7 +246,7 @@ extern "C" int emu_ttf(int nz, int nx, const double *veln, const int32_t *velpn,
             bg.nz = g.nz; bg.nx = g.nx; bg.T = g.t; bg.dnx = g.dnx; bg.mv = g.mv;
             std::fill(lalive.begin(), lalive.begin() + (size_t)g.nz * g.nx, (uint8_t)ALI_ST_FAR);
             ldirty.assign(ali_dirty_bytes(g.nz, g.nx), 0);
-            bg.st = lalive.data(); bg.dirty = ldirty.data(); bg.tiles_x = ali_dirty_tiles_x(g.nx);
+            bg.st = lalive.data(); bg.dirty = ldirty.data(); bg.tiles_x = ali_dirty_tiles_x(g.nx); bg.t4x = 0;
             std::vector<unsigned> list;
             seq_to_band(g, bg, list);
             int mask = ali_level_stop_mask(g.nz, g.nx, s.cz[l & 1], s.cx[l & 1], p.scale[l] * p.size[l]);
@@ -261,10 +264,10 @@ extern "C" int emu_ttf(int nz, int nx, const double *veln, const int32_t *velpn,
             fclose(f);
         }
     }
-    ali_src_main_geometry(s, m, p, sc, T);
+    ali_src_main_geometry(s, m, p, sc);
     counters[7] = s.overflow;
     if (s.overflow) return -1;
-    ali_seq_clear(s.mg, false, 0, 1);
+    ali_seq_clear(s.mg, true, 0, 1);
     if (coop) {
         const int last = (p.nlev - 1) & 1;
         ali_seq_handoff(s.lv[last], s.cz[last], s.cx[last], s.mg, p.isz, p.isx);
@@ -279,14 +282,28 @@ extern "C" int emu_ttf(int nz, int nx, const double *veln, const int32_t *velpn,
     if (s.overflow) return -1;
 
     // ---- band-synchronous march of the main grid (replay of the kernel's round loop) ----
-    std::vector<uint8_t> status(n, ALI_ST_FAR), dirty(ali_dirty_bytes(p.nz, p.nx), 0);
+    // the kernel's tiled field layout can be replayed too (g_tiled): same result, un-tiled at the end
+    const size_t nt = g_tiled ? ali_field_nodes_tiled(p.nz, p.nx) : n;
+    std::vector<uint8_t> status(nt, ALI_ST_FAR), dirty(ali_dirty_bytes(p.nz, p.nx), 0);
+    std::vector<double> Tt;
     AliBandGrid bg;
-    bg.nz = p.nz; bg.nx = p.nx; bg.T = T; bg.st = status.data(); bg.dirty = dirty.data(); bg.dnx = m.dnx;
+    bg.nz = p.nz; bg.nx = p.nx; bg.st = status.data(); bg.dirty = dirty.data(); bg.dnx = m.dnx;
     bg.tiles_x = ali_dirty_tiles_x(p.nx);
+    bg.t4x = g_tiled ? (p.nx + 3) / 4 : 0;
+    if (g_tiled) {
+        Tt.resize(nt);
+        std::memset(Tt.data(), ALI_T_UNSET_BYTE, nt * sizeof(double));
+        bg.T = Tt.data();
+    } else {
+        bg.T = T;
+    }
     bg.mv = ali_band_view(sg);
     std::vector<unsigned> list;
     seq_to_band(s.mg, bg, list);
     band_run(m, bg, list, delta, 0, eager != 0, mst);
+    if (g_tiled)
+        for (int z = 0; z < p.nz; z++)
+            for (int x = 0; x < p.nx; x++) T[(size_t)z * p.nx + x] = Tt[bg.ti(z, x)];
     for (size_t i = 0; i < n; i++) T[i] = (T[i] >= 0.0) ? T[i] / p.sg : 0.0; // ATR:2832
     counters[3] = mst.rounds; counters[4] = mst.evals; counters[5] = mst.fbs + lst.fbs; counters[6] = mst.maxlist;
     counters[8] = lst.rounds; counters[9] = lst.evals;

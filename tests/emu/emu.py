@@ -41,6 +41,11 @@ def set_coop(nlanes):
     lib().emu_set_coop(int(nlanes))
 
 
+def set_tiled(on):
+    """Replays the band march on the kernel's 4 x 4-tiled field layout (default: row-major)."""
+    lib().emu_set_tiled(int(bool(on)))
+
+
 def model_vmax(m, dnx):
     return lib().emu_model_vmax(*_margs(m, dnx))
 
