@@ -53,7 +53,8 @@ struct AliBandGrid {
     double dnx;
     ALI_DEV size_t ti(int z, int x) const
     {
-        if (t4x) return ((((size_t)(z >> 2) * (size_t)t4x + (size_t)(x >> 2)) << 4) | (size_t)(((z & 3) << 2) | (x & 3)));
+        // 32-bit arithmetic: a field has fewer than 2^31 nodes (checked by alifmm_ttf), tile padding adds < 1 %
+        if (t4x) return (size_t)(((((unsigned)z >> 2) * (unsigned)t4x + ((unsigned)x >> 2)) << 4) | (((unsigned)z & 3u) << 2) | ((unsigned)x & 3u));
         return (size_t)z * nx + x;
     }
     ALI_DEV bool avail(int z, int x) const { return T[ti(z, x)] >= 0.0; } // false for NaN
@@ -194,10 +195,19 @@ ALI_DEV bool ali_band_claim(const AliBandGrid &g, size_t node)
 ALI_DEV int ali_band_accept(const AliBandGrid &g, int iz, int ix, unsigned *nb)
 {
     int cnt = 0;
-    g.st[g.ti(iz, ix)] = ALI_ST_ALIVE;
+    const size_t me = g.ti(iz, ix);
+    g.st[me] = ALI_ST_ALIVE;
     const bool hw = ix > 0, he = ix < g.nx - 1, hn = iz > 0, hs = iz < g.nz - 1;
-    const size_t nw = hw ? g.ti(iz, ix - 1) : 0, ne = he ? g.ti(iz, ix + 1) : 0;
-    const size_t nn = hn ? g.ti(iz - 1, ix) : 0, ns = hs ? g.ti(iz + 1, ix) : 0;
+    size_t nw, ne, nn, ns;
+    if (g.t4x) {   // step inside the tile, or to the facing edge of the next tile
+        const size_t trow = (size_t)g.t4x << 4;
+        nw = (ix & 3) ? me - 1 : me - 13;
+        ne = ((ix & 3) != 3) ? me + 1 : me + 13;
+        nn = (iz & 3) ? me - 4 : me - trow + 12;
+        ns = ((iz & 3) != 3) ? me + 4 : me + trow - 12;
+    } else {
+        nw = me - 1; ne = me + 1; nn = me - g.nx; ns = me + g.nx;
+    }
 #if defined(__CUDA_ARCH__)
     // the four state words are loaded together (one memory latency), then only far ones are claimed
     const volatile unsigned long long *tw = (const volatile unsigned long long *)g.T;

@@ -961,7 +961,8 @@ extern "C" int alifmm_set_option(alifmm_ctx *c, const char *name, double value)
         c->band_cap_factor = value;
     } else if (!strcmp(name, "threads_per_source")) {
         int t = (int)value;
-        if (t != 256 && t != 512 && t != 1024) return fail(ALIFMM_E_INVALID, "threads_per_source must be 256, 512 or 1024");
+        if (t != 256 && t != 512 && t != 768 && t != 1024)
+            return fail(ALIFMM_E_INVALID, "threads_per_source must be 256, 512, 768 or 1024");
         c->threads_per_source = t;
     } else if (!strcmp(name, "resort_every")) {
         if (value < 0 || value > 1000000) return fail(ALIFMM_E_INVALID, "resort_every must be >= 0");
@@ -1069,6 +1070,9 @@ static int ttf_attempt(alifmm_ctx *c, int32_t n_src, const int32_t *src_iz, cons
         if (c->threads_per_source >= 1024) {
             CUDA_TRY(cudaFuncSetAttribute(ali_march_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             ali_march_kernel<1024><<<n_src, 1024, smem, s>>>(b, smem_cap);
+        } else if (c->threads_per_source >= 768) {
+            CUDA_TRY(cudaFuncSetAttribute(ali_march_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ali_march_kernel<768><<<n_src, 768, smem, s>>>(b, smem_cap);
         } else if (c->threads_per_source >= 512) {
             CUDA_TRY(cudaFuncSetAttribute(ali_march_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             ali_march_kernel<512><<<n_src, 512, smem, s>>>(b, smem_cap);

@@ -250,3 +250,20 @@ def test_replay_deviations_start_at_reference_glitches():
     # and before that moment the two solutions are bit-identical
     earlier = ref < ref[z, x]
     assert np.array_equal(ref[earlier], T[earlier])
+
+
+@pytest.mark.parametrize("sg,src", [(3, (0, 40)), (1, (30, 41)), (3, (60, 82))])
+def test_replay_tiled_field_layout_equals_row_major(sg, src):
+    """The kernel marches on a field of 4 x 4-node tiles (ali_band.cuh); the replay on that
+    layout -- extents that are not multiples of 4 included -- gives the row-major result bit for bit."""
+    m = models.weld_crop(61, 83)
+    om = _model(m)
+    try:
+        emu.set_tiled(False)
+        A, ca, rca = emu.ttf(om, m["dnx"], src[0], src[1], sg)
+        emu.set_tiled(True)
+        B, cb, rcb = emu.ttf(om, m["dnx"], src[0], src[1], sg)
+    finally:
+        emu.set_tiled(False)
+    assert rca == 0 and rcb == 0 and np.array_equal(A, B)
+    assert ca["rounds"] == cb["rounds"] and ca["band_evals"] == cb["band_evals"]
