@@ -113,6 +113,7 @@ def test_replay_last_ulp_sensitivity():
     om2 = _model(m)
     ref2 = orc.travel(om2, m["dnx"] * 100, m["dnx"] * 1, m["dnx"])
     try:
+        emu.set_coop(0)   # noise on the reference's own evaluation sequence (speculation would draw other noise)
         worst2 = 0.0
         for seed in (7920, 15839, 23758):
             emu.set_noise(0.3, seed)
@@ -125,6 +126,7 @@ def test_replay_last_ulp_sensitivity():
         assert worst2 > 1e-9   # the homogeneous medium IS sensitive
     finally:
         emu.set_noise(0.0)
+        emu.set_coop(32)
 
 
 def test_replay_last_ulp_sensitivity_of_symmetric_media():
@@ -139,10 +141,12 @@ def test_replay_last_ulp_sensitivity_of_symmetric_media():
     T, _, _ = emu.ttf(om, m["dnx"], 100, 1, 1)
     assert models.rel_err(ref, T).max() <= 1e-12          # same libm: exact
     try:
+        emu.set_coop(0)
         emu.set_noise(0.05, 12345)
         T, _, _ = emu.ttf(om, m["dnx"], 100, 1, 1)
     finally:
         emu.set_noise(0.0)
+        emu.set_coop(32)
     e = models.rel_err(ref, T)
     assert (e > 1e-5).mean() > 0.2 and 1e-3 < e.max() < 5e-2 and e.mean() < 2e-4
 
