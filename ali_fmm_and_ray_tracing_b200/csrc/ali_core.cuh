@@ -25,14 +25,26 @@
 #define ALI_HD inline
 #endif
 
-// Transcendentals go through these macros so that the host replay (tests/emu) can inject
-// last-ulp noise and measure how sensitive a solution is to the libm in use.
+// Transcendentals: on the device the accurate versions of ali_crmath.cuh (they agree with the
+// glibc results the reference sees in 99.9 % of the calls; CUDA's libm does not).  The host replay
+// (tests/emu) routes them through hooks so that it can use glibc (the reference's libm), the same
+// accurate versions (bit-identical to the device), or inject last-ulp noise to measure how
+// sensitive a solution is.
+#include "ali_crmath.cuh"
 #if defined(ALI_EMU_NOISE) && !defined(__CUDACC__)
-double ali_emu_noise(double v);
-#define ALI_ATAN(x) ali_emu_noise(atan(x))
-#define ALI_SIN(x) ali_emu_noise(sin(x))
-#define ALI_COS(x) ali_emu_noise(cos(x))
-#define ALI_TAN(x) ali_emu_noise(tan(x))
+double ali_emu_atan(double x);
+double ali_emu_sin(double x);
+double ali_emu_cos(double x);
+double ali_emu_tan(double x);
+#define ALI_ATAN(x) ali_emu_atan(x)
+#define ALI_SIN(x) ali_emu_sin(x)
+#define ALI_COS(x) ali_emu_cos(x)
+#define ALI_TAN(x) ali_emu_tan(x)
+#elif defined(__CUDACC__) && !defined(ALI_LIBM_MATH)
+#define ALI_ATAN(x) ali_cr_atan(x)
+#define ALI_SIN(x) ali_cr_sin(x)
+#define ALI_COS(x) ali_cr_cos(x)
+#define ALI_TAN(x) ali_cr_tan(x)
 #else
 #define ALI_ATAN(x) atan(x)
 #define ALI_SIN(x) sin(x)

@@ -225,6 +225,7 @@ struct AliSeqCounters {
     long long pops, evals, fallbacks;
     long long cyc_heap, cyc_eval;   // device builds: SM cycles in heap operations / evaluations
     long long steps, computed;      // cooperative march: warp-wide evaluation steps, evaluations executed in them
+    long long cyc_total, cyc_fill, cyc_start;   // device builds: whole source / fills + seeds / perimeter push + hand-offs
 };
 
 #if defined(__CUDA_ARCH__)
@@ -764,6 +765,7 @@ ALI_DEV void ali_src_begin(AliSrcState &s, const AliSourcePlan &p)
     s.cnt.pops = s.cnt.evals = s.cnt.fallbacks = 0;
     s.cnt.cyc_heap = s.cnt.cyc_eval = 0;
     s.cnt.steps = s.cnt.computed = 0;
+    s.cnt.cyc_total = s.cnt.cyc_fill = s.cnt.cyc_start = 0;
     s.overflow = 0;
     s.base = ali_make_view(1, 0, 0, p.fine ? p.sg : 1, p.fine ? 1 : 0);
 }
@@ -874,13 +876,18 @@ ALI_DEV void ali_seq_source(const AliModel &m, const AliSourcePlan &p, const Ali
 {
     AliSrcState s;
     const bool coop = sc.cval != nullptr;
+    const long long t_begin = ALI_CLOCK();
     ali_src_begin(s, p);
     for (int l = 0; l < p.nlev; l++) {
+        long long t0 = ALI_CLOCK();
         ali_src_level_geometry(s, m, p, sc, l);
         ali_src_level_fill(s, m, p, l, lane, nlanes, true);
         ALI_SYNCWARP();
+        long long t1 = ALI_CLOCK();
         if (lane == 0) ali_src_level_start(s, p, l);
         ALI_SYNCWARP();
+        s.cnt.cyc_fill += t1 - t0;
+        s.cnt.cyc_start += ALI_CLOCK() - t1;
         if (coop) ali_src_level_seq_coop(s, m, p, l, lane, nlanes);
         else if (lane == 0) ali_src_level_seq(s, m, p, l, -1);
         ALI_SYNCWARP();
@@ -890,16 +897,21 @@ ALI_DEV void ali_seq_source(const AliModel &m, const AliSourcePlan &p, const Ali
     s.overflow = __shfl_sync(0xffffffffu, s.overflow, 0);
 #endif
     if (!s.overflow) {
+        long long t0 = ALI_CLOCK();
         ali_seq_clear(s.mg, true, lane, nlanes);
         ALI_SYNCWARP();
+        long long t1 = ALI_CLOCK();
         const int last = (p.nlev - 1) & 1;
         if (lane == 0) ali_seq_handoff(s.lv[last], s.cz[last], s.cx[last], s.mg, p.isz, p.isx);
         ALI_SYNCWARP();
+        s.cnt.cyc_fill += t1 - t0;
+        s.cnt.cyc_start += ALI_CLOCK() - t1;
         if (coop) ali_seq_march_coop(s.mg, m, p.isx, p.isz, -1, 0, p.stop_r, s.cnt, lane, nlanes);
         else if (lane == 0) ali_seq_march(s.mg, m, p.isx, p.isz, -1, 0, p.stop_r, s.cnt);
         s.overflow |= s.mg.overflow;
         ALI_SYNCWARP();
     }
+    s.cnt.cyc_total = ALI_CLOCK() - t_begin;
     res.wz0 = s.mg.wz0; res.wx0 = s.mg.wx0; res.wnz = s.mg.wnz; res.wnx = s.mg.wnx;
     res.overflow = s.overflow;
     res.cnt = s.cnt;

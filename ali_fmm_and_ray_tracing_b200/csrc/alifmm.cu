@@ -1119,9 +1119,22 @@ static int ttf_attempt(alifmm_ctx *c, int32_t n_src, const int32_t *src_iz, cons
     }
     if (getenv("ALIFMM_DEBUG")) {
         const AliSourceRec &r = recs[0];
-        fprintf(stderr, "[alifmm] source 0 seq: pops %lld evals %lld, steps %lld computed %lld, cycles/pop walk %.0f, cycles/step %.0f\n", r.seq.cnt.pops,
+        fprintf(stderr, "[alifmm] source 0 seq: pops %lld evals %lld, steps %lld computed %lld, cycles/pop walk %.0f, cycles/step %.0f; Mcycles total %.0f fills %.0f starts %.0f\n", r.seq.cnt.pops,
                 r.seq.cnt.evals, r.seq.cnt.steps, r.seq.cnt.computed, (double)r.seq.cnt.cyc_heap / (r.seq.cnt.pops + 1e-9),
-                (double)r.seq.cnt.cyc_eval / (r.seq.cnt.steps + 1e-9));
+                (double)r.seq.cnt.cyc_eval / (r.seq.cnt.steps + 1e-9), r.seq.cnt.cyc_total * 1e-6, r.seq.cnt.cyc_fill * 1e-6,
+                r.seq.cnt.cyc_start * 1e-6);
+        {
+            int kmax = 0, kmin = 0;
+            for (size_t k = 0; k < recs.size(); k++) {
+                if (recs[k].seq.cnt.cyc_total > recs[kmax].seq.cnt.cyc_total) kmax = (int)k;
+                if (recs[k].seq.cnt.cyc_total < recs[kmin].seq.cnt.cyc_total) kmin = (int)k;
+            }
+            for (int k : {kmin, kmax})
+                fprintf(stderr, "[alifmm] seq %s source %d (z=%d,x=%d): Mcycles %.0f, pops %lld steps %lld, walk/pop %.0f, cycles/step %.0f\n",
+                        k == kmin ? "fastest" : "slowest", k, recs[k].src_iz, recs[k].src_ix, recs[k].seq.cnt.cyc_total * 1e-6,
+                        recs[k].seq.cnt.pops, recs[k].seq.cnt.steps, (double)recs[k].seq.cnt.cyc_heap / (recs[k].seq.cnt.pops + 1e-9),
+                        (double)recs[k].seq.cnt.cyc_eval / (recs[k].seq.cnt.steps + 1e-9));
+        }
         fprintf(stderr, "[alifmm] source 0: rounds %lld, cycles/round A %.0f B %.0f C %.0f sort %.0f, evals/round %.0f, band max %lld\n",
                 r.rounds, (double)r.cycles[0] / (r.rounds + 1e-9), (double)r.cycles[1] / (r.rounds + 1e-9),
                 (double)r.cycles[2] / (r.rounds + 1e-9), (double)r.cycles[3] / (r.rounds + 1e-9),

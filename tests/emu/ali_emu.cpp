@@ -29,6 +29,19 @@ double ali_emu_noise(double v)
 }
 extern "C" void emu_set_noise(double p, unsigned long long seed) { g_noise_p = p; if (seed) g_noise_state = seed; }
 
+// Which sin / cos / tan / atan the replay uses: 0 = glibc (what the reference runs on), 1 = the
+// device's accurate versions (csrc/ali_crmath.cuh; then the replay and the kernels produce the same bits).
+static int g_crmath = 0;
+extern "C" void emu_set_crmath(int on) { g_crmath = on; }
+extern "C" double emu_crmath_eval(int fn, double x)   // 0 atan, 1 sin, 2 cos, 3 tan
+{
+    return fn == 0 ? ali_cr_atan(x) : fn == 1 ? ali_cr_sin(x) : fn == 2 ? ali_cr_cos(x) : ali_cr_tan(x);
+}
+double ali_emu_atan(double x) { return ali_emu_noise(g_crmath ? ali_cr_atan(x) : atan(x)); }
+double ali_emu_sin(double x) { return ali_emu_noise(g_crmath ? ali_cr_sin(x) : sin(x)); }
+double ali_emu_cos(double x) { return ali_emu_noise(g_crmath ? ali_cr_cos(x) : cos(x)); }
+double ali_emu_tan(double x) { return ali_emu_noise(g_crmath ? ali_cr_tan(x) : tan(x)); }
+
 struct HostModel {
     std::vector<AliMatRec> rec;
     AliModel m;

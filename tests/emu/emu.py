@@ -41,6 +41,12 @@ def set_coop(nlanes):
     lib().emu_set_coop(int(nlanes))
 
 
+def set_crmath(on):
+    """sin / cos / tan / atan of the replay: False = glibc (the reference's libm, default), True = the device's
+    accurate versions (csrc/ali_crmath.cuh) -- the replay then reproduces the kernels bit for bit."""
+    lib().emu_set_crmath(int(bool(on)))
+
+
 def set_tiled(on):
     """Replays the band march on the kernel's 4 x 4-tiled field layout (default: row-major)."""
     lib().emu_set_tiled(int(bool(on)))

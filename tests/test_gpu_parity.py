@@ -86,15 +86,20 @@ def test_notebook_fields_match_oracle_and_golden(capi, orc, name):
         ref = orc.travel(om, m["scx"][k], m["scz"][k], m["dnx"])
         if name == "gradient":
             assert models.rel_err(ref, T[k]).max() <= TOL_EXACT
-        elif name == "christoffel":   # homogeneous: a few last-ulp ties
-            _check_field(ref, T[k], what=(name, k))
+        elif name == "christoffel":
+            # homogeneous: exact ties between stencils; with the device's accurate atan / sin / cos
+            # (csrc/ali_crmath.cuh) they resolve as on glibc: measured max 3e-10
+            assert models.rel_err(ref, T[k]).max() <= 1e-8, (name, k)
         else:
             # homogeneous AND axis-aligned: stencil ties everywhere; the reference itself moves by
-            # ~5e-3 on ~40 % of the nodes when atan changes in the last ulp (test_kernel_replay.py::
-            # test_replay_last_ulp_sensitivity_of_symmetric_media), so only the scheme's own
-            # accuracy level can be asserted
+            # ~5e-3 on ~40 % of the nodes when atan changes in the last ulp of 5 % of the calls
+            # (test_kernel_replay.py::test_replay_last_ulp_sensitivity_of_symmetric_media).  The
+            # accurate device functions differ from glibc in 0.03-0.14 % of the calls: the first field
+            # comes out bit-identical, the second still meets one such tie (94 % within 1e-5)
             e = models.rel_err(ref, T[k])
             assert e.mean() <= 2e-4 and e.max() <= 5e-2, (name, k, e.mean(), e.max())
+            if k == 0:
+                assert e.max() <= TOL_EXACT
         assert T[k][iz[k], ix[k]] == 0.0
     gold = _load("golden_fields.npz")
     if name == "gradient":   # straight from the reference (notebook cell 12)
@@ -136,8 +141,39 @@ def test_edge_and_corner_sources(capi, orc):
     om = _omodel(orc, m)
     for k in range(len(pts)):
         ref = orc.travel(om, m["dnx"] * ix[k], m["dnx"] * iz[k], m["dnx"])
-        _check_field(ref, T[k], frac=0.995, what=pts[k])
+        # homogeneous medium, exact stencil ties: identical to the reference to rounding level since the
+        # device's atan / sin / cos agree with glibc (with CUDA's libm two of these sources moved by 1e-4)
+        assert models.rel_err(ref, T[k]).max() <= 1e-12, pts[k]
     ctx.close()
+
+
+def test_kernels_equal_host_replay_bit_for_bit(capi, orc):
+    """The kernels against the host replay of the same source files run on the same accurate
+    sin / cos / tan / atan (csrc/ali_crmath.cuh; fma() is exact on both sides): every bit equal --
+    the sequential phase, the band march on the tiled field, the finalize pass.  This separates
+    'the GPU implements the algorithm' (here, exact) from 'the algorithm reproduces the reference'
+    (the replay tests on glibc, exact away from reference heap glitches)."""
+    from tests.emu import emu
+    cases = []
+    v = models.voronoi(512, 64, 1234)
+    sx, sz = models.lattice_sources(512, v["dnx"], rows=2, cols=2)
+    cases.append((v, [(int(round(z / v["dnx"])), int(round(x / v["dnx"]))) for x, z in zip(sx, sz)], 1))
+    cases.append((models.weld_crop(120, 160), [(0, 40), (119, 100), (60, 80)], 3))
+    h = models.notebook_christoffel(101)
+    h["veln"] = 35.0 * np.ones((101, 101))
+    cases.append((h, [(0, 50), (99, 99), (2, 97), (50, 50)], 1))
+    try:
+        emu.set_crmath(True)
+        for m, srcs, sg in cases:
+            ctx = _ctx(capi, m)
+            om = _omodel(orc, m)
+            T = ctx.ttf(np.array([s[0] for s in srcs], dtype=np.int32), np.array([s[1] for s in srcs], dtype=np.int32), sg)
+            for k, s in enumerate(srcs):
+                R, _, rc = emu.ttf(om, m["dnx"], s[0], s[1], sg)
+                assert rc == 0 and np.array_equal(R, T[k]), (s, sg, models.rel_err(R, T[k]).max())
+            ctx.close()
+    finally:
+        emu.set_crmath(False)
 
 
 # ----------------------------------------------------------------------------- BASELINE configs 3, 4, 5

@@ -271,3 +271,37 @@ def test_replay_tiled_field_layout_equals_row_major(sg, src):
         emu.set_tiled(False)
     assert rca == 0 and rcb == 0 and np.array_equal(A, B)
     assert ca["rounds"] == cb["rounds"] and ca["band_evals"] == cb["band_evals"]
+
+
+def test_device_math_agrees_with_glibc():
+    """csrc/ali_crmath.cuh (compiled for the host by the replay tool): the accurate sin / cos / tan /
+    atan the kernels use return glibc's result -- what the reference computes with -- in all but
+    ~0.1 % of the calls (glibc itself misses the correctly rounded value that often), never by more
+    than one ulp; and a replay on those functions equals the replay on glibc on the regular media."""
+    import ctypes
+    lib = emu.lib()
+    lib.emu_crmath_eval.restype = ctypes.c_double
+    lib.emu_crmath_eval.argtypes = [ctypes.c_int, ctypes.c_double]
+    rng = np.random.default_rng(3)
+    n = 200000
+    args = {0: np.tan(rng.uniform(-1.55, 1.55, n)), 1: rng.uniform(-3.1, 6.28, n), 2: rng.uniform(-3.1, 6.28, n),
+            3: rng.uniform(0.001, 3.14, n)}
+    import math
+    ref = {0: math.atan, 1: math.sin, 2: math.cos, 3: math.tan}   # C libm (numpy may use its own SIMD kernels)
+    for fn in range(4):
+        got = np.array([lib.emu_crmath_eval(fn, float(x)) for x in args[fn]])
+        want = np.array([ref[fn](float(x)) for x in args[fn]])
+        diff = got != want
+        assert diff.mean() <= (5e-3 if fn == 3 else 2.5e-3), (fn, diff.mean())
+        assert (np.abs(got - want)[diff] <= np.spacing(np.abs(want[diff])) * 1.0000001).all()
+    for fn, x, y in ((0, 0.0, 0.0), (0, 1.0, math.atan(1.0)), (0, -1e30, -math.pi / 2), (1, 0.0, 0.0), (2, 0.0, 1.0), (3, 0.0, 0.0)):
+        assert lib.emu_crmath_eval(fn, x) == y
+    m = models.weld_crop(60, 80)
+    om = _model(m)
+    try:
+        A, _, _ = emu.ttf(om, m["dnx"], 0, 40, 3)
+        emu.set_crmath(True)
+        B, _, _ = emu.ttf(om, m["dnx"], 0, 40, 3)
+    finally:
+        emu.set_crmath(False)
+    assert models.rel_err(A, B).max() <= 1e-13
