@@ -40,16 +40,19 @@ double ali_emu_tan(double x);
 #define ALI_SIN(x) ali_emu_sin(x)
 #define ALI_COS(x) ali_emu_cos(x)
 #define ALI_TAN(x) ali_emu_tan(x)
+#define ALI_SINCOS(tab, x, s, c) do { (void)(tab); (c) = ali_emu_cos(x); (s) = ali_emu_sin(x); } while (0)
 #elif defined(__CUDACC__) && !defined(ALI_LIBM_MATH)
 #define ALI_ATAN(x) ali_cr_atan(x)
 #define ALI_SIN(x) ali_cr_sin(x)
 #define ALI_COS(x) ali_cr_cos(x)
 #define ALI_TAN(x) ali_cr_tan(x)
+#define ALI_SINCOS(tab, x, s, c) ali_cr_sincos((tab), (x), (s), (c))
 #else
 #define ALI_ATAN(x) atan(x)
 #define ALI_SIN(x) sin(x)
 #define ALI_COS(x) cos(x)
 #define ALI_TAN(x) tan(x)
+#define ALI_SINCOS(tab, x, s, c) do { (void)(tab); (c) = cos(x); (s) = sin(x); } while (0)
 #endif
 
 #define ALI_PI 3.14159265358979323846
@@ -75,6 +78,7 @@ struct AliModel {
     int has_stif;            // reference's "stif_den is not None"
     const double *group_tab; // [361*ncol]
     const double *phase_tab; // [361*ncol]
+    const double *sincos_tab; // nullptr, or a copy of ali_cr_sincos_tab in faster memory (set by the band march)
     int ncol;
     double dnx;
 };
@@ -185,10 +189,10 @@ ALI_DEV double ali_table_vel(const double *tab, int ncol, double eff, int col, d
 }
 
 // Christoffel phase velocity, stiffness in MPa (ATR:1400-1406).
-ALI_DEV double ali_christoffel_phase(double eff, const double *s, double vm)
+ALI_DEV double ali_christoffel_phase(double eff, const double *s, double vm, const double *sincos_tab = nullptr)
 {
-    double c = ALI_COS(ALI_DEG2RAD * eff);
-    double sn = ALI_SIN(ALI_DEG2RAD * eff);
+    double c, sn;
+    ALI_SINCOS(sincos_tab, ALI_DEG2RAD * eff, sn, c);
     double A = c * c * s[0] + sn * sn * s[3];
     double B = c * sn * (s[1] + s[3]);
     double C = c * c * s[3] + sn * sn * s[2];
@@ -223,7 +227,7 @@ ALI_DEV double ali_christoffel_group(double eff, const double *s, double vm)
 ALI_DEV double ali_phase_velocity(const AliModel &m, const AliMat &mat, double eff)
 {
     if (mat.velpn != 0 || !m.has_stif) return ali_table_vel(m.phase_tab, m.ncol, eff, mat.velpn, mat.vel_map);
-    return ali_christoffel_phase(eff, mat.s, mat.vel_map);
+    return ali_christoffel_phase(eff, mat.s, mat.vel_map, m.sincos_tab);
 }
 
 ALI_DEV double ali_group_velocity(const AliModel &m, const AliMat &mat, double eff)

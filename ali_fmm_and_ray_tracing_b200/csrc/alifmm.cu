@@ -206,6 +206,8 @@ __device__ __forceinline__ int ali_sort_bin(unsigned e, int isz, int isx)
 // published node and a global load + store per band node per round.
 #define ALI_DMAP_BITS 9
 #define ALI_DMAP_WORDS ((1 << (2 * ALI_DMAP_BITS)) / 32)
+#define ALI_MARCH_SMEM_DMAP (ALI_DMAP_WORDS * 4)
+#define ALI_MARCH_SMEM_FIXED (ALI_MARCH_SMEM_DMAP + 404 * 4 * 8)
 __device__ __forceinline__ void ali_dmap_row(unsigned *dmap, int z, int x0, unsigned pattern)
 {
     const unsigned m = (1u << ALI_DMAP_BITS) - 1u;
@@ -238,7 +240,11 @@ __device__ __forceinline__ bool ali_dmap_test(const unsigned *dmap, int iz, int 
 template <int NT>
 __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
 {
+    // dynamic shared memory: window-change bitmap | sin/cos table (csrc/ali_crmath.cuh) | optional band lists
     extern __shared__ __align__(16) unsigned char s_raw[];
+    unsigned *s_dmap = reinterpret_cast<unsigned *>(s_raw);
+    double *s_sincos = reinterpret_cast<double *>(s_raw + ALI_MARCH_SMEM_DMAP);
+    unsigned char *s_lists = s_raw + ALI_MARCH_SMEM_FIXED;
     const int src = blockIdx.x;
     const int tid = threadIdx.x;
     AliSourceRec &rec = b.rec[src];
@@ -250,7 +256,6 @@ __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
     __shared__ AliBandGrid s_grid;   // copy for the out-of-line FD fallback
     __shared__ int s_bins[ALI_SORT_BINS];
     __shared__ int s_wsum[32];
-    __shared__ __align__(16) unsigned s_dmap[ALI_DMAP_WORDS];
     __shared__ int s_force[2];   // by round parity: re-evaluate the whole band (FD fallback outside the register path)
     long long cyc[4] = {0, 0, 0, 0};
     const int isz = (b.sg > 1 ? b.sg : 1) * rec.src_iz, isx = (b.sg > 1 ? b.sg : 1) * rec.src_ix;
@@ -270,13 +275,16 @@ __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
     double *val0 = b.stage + (size_t)src * 2 * cap, *val1 = val0 + cap;
     unsigned *ent0, *ent1, *wrk0, *wrk1;
     if (smem_cap >= cap) {
-        ent0 = (unsigned *)s_raw; ent1 = ent0 + cap;
+        ent0 = (unsigned *)s_lists; ent1 = ent0 + cap;
         wrk0 = ent1 + cap; wrk1 = wrk0 + cap;
     } else {
         ent0 = b.lists + (size_t)src * 4 * cap; ent1 = ent0 + cap;
         wrk0 = ent1 + cap; wrk1 = wrk0 + cap;
     }
 
+    for (int q = tid; q < 404 * 4; q += NT) s_sincos[q] = ali_cr_sincos_tab[q];
+    AliModel mdl = b.m;
+    mdl.sincos_tab = s_sincos;
     if (tid == 0) {
         s_grid = g;
         s_count[0] = 0; s_count[1] = 0; s_nwork[0] = 0; s_nwork[1] = 0;
@@ -352,7 +360,7 @@ __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
             const int iz = ALI_PACK_Z(e), ix = ALI_PACK_X(e);
             int fb = 0;
             const double vold = val[i];   // the value this node last published (0: none yet)
-            const double v = ali_band_eval(b.m, b.m_dev, g, &s_grid, iz, ix, &fb);
+            const double v = ali_band_eval(mdl, b.m_dev, g, &s_grid, iz, ix, &fb);
             val[i] = v;
             my_evals++;
             my_fbs += fb;
@@ -968,7 +976,7 @@ extern "C" int alifmm_set_option(alifmm_ctx *c, const char *name, double value)
         if (value < 0 || value > 1000000) return fail(ALIFMM_E_INVALID, "resort_every must be >= 0");
         c->resort_every = (int)value;
     } else if (!strcmp(name, "band_smem_kb")) {
-        if (value < 0 || value > 200) return fail(ALIFMM_E_INVALID, "band_smem_kb must be in [0, 200]");
+        if (value < 0 || value > 180) return fail(ALIFMM_E_INVALID, "band_smem_kb must be in [0, 180]");
         c->band_smem_bytes = (int)value * 1024;
     } else {
         return fail(ALIFMM_E_INVALID, std::string("unknown option ") + name);
@@ -1066,7 +1074,7 @@ static int ttf_attempt(alifmm_ctx *c, int32_t n_src, const int32_t *src_iz, cons
         // band entries + work lists in shared memory when they fit in c->band_smem_bytes
         size_t need = (size_t)b.band_cap * 16;
         int smem_cap = need <= (size_t)c->band_smem_bytes ? b.band_cap : 0;
-        size_t smem = smem_cap ? need : 0;
+        size_t smem = (smem_cap ? need : 0) + ALI_MARCH_SMEM_FIXED;
         if (c->threads_per_source >= 1024) {
             CUDA_TRY(cudaFuncSetAttribute(ali_march_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             ali_march_kernel<1024><<<n_src, 1024, smem, s>>>(b, smem_cap);
