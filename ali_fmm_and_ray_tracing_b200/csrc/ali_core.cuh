@@ -220,7 +220,9 @@ ALI_DEV double ali_christoffel_group(double eff, const double *s, double vm)
         ph = ali_pymod(ALI_ATAN((-B - disc) / (C - A)), ALI_PI);
     else
         ph = ali_pymod(ALI_ATAN((-B + disc) / (C - A)), ALI_PI);
-    double lam = 0.5 * (ALI_COS(2 * ph) * (c22 - c44) + ALI_SIN(2 * ph) * (c23 + c44) * t + c22 + c44);
+    double c2, s2;
+    ALI_SINCOS(nullptr, 2 * ph, s2, c2);
+    double lam = 0.5 * (c2 * (c22 - c44) + s2 * (c23 + c44) * t + c22 + c44);
     return 1000 * vm * sqrt(lam / s[4]) / ALI_COS(ALI_DEG2RAD * eff - ph);
 }
 
