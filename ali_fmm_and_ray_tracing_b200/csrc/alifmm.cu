@@ -739,7 +739,7 @@ struct alifmm_ctx {
     double delta_frac = 0.3;
     int margin = 27;
     double band_cap_factor = 6.0;
-    int threads_per_source = 1024;
+    int threads_per_source = 768;   // 80 registers per thread: fewer spills than 1024 x 64, more warps than 512 x 128 (measured)
     int resort_every = 8;
     int band_smem_bytes = 0;   // measured on B200: L1 for the T / status gathers is worth more than smem lists
     // resident batch
@@ -969,8 +969,8 @@ extern "C" int alifmm_set_option(alifmm_ctx *c, const char *name, double value)
         c->band_cap_factor = value;
     } else if (!strcmp(name, "threads_per_source")) {
         int t = (int)value;
-        if (t != 256 && t != 512 && t != 768 && t != 1024)
-            return fail(ALIFMM_E_INVALID, "threads_per_source must be 256, 512, 768 or 1024");
+        if (t != 256 && t != 512 && t != 640 && t != 768 && t != 896 && t != 1024)
+            return fail(ALIFMM_E_INVALID, "threads_per_source must be 256, 512, 640, 768, 896 or 1024");
         c->threads_per_source = t;
     } else if (!strcmp(name, "resort_every")) {
         if (value < 0 || value > 1000000) return fail(ALIFMM_E_INVALID, "resort_every must be >= 0");
@@ -1078,9 +1078,15 @@ static int ttf_attempt(alifmm_ctx *c, int32_t n_src, const int32_t *src_iz, cons
         if (c->threads_per_source >= 1024) {
             CUDA_TRY(cudaFuncSetAttribute(ali_march_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             ali_march_kernel<1024><<<n_src, 1024, smem, s>>>(b, smem_cap);
+        } else if (c->threads_per_source >= 896) {
+            CUDA_TRY(cudaFuncSetAttribute(ali_march_kernel<896>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ali_march_kernel<896><<<n_src, 896, smem, s>>>(b, smem_cap);
         } else if (c->threads_per_source >= 768) {
             CUDA_TRY(cudaFuncSetAttribute(ali_march_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             ali_march_kernel<768><<<n_src, 768, smem, s>>>(b, smem_cap);
+        } else if (c->threads_per_source >= 640) {
+            CUDA_TRY(cudaFuncSetAttribute(ali_march_kernel<640>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ali_march_kernel<640><<<n_src, 640, smem, s>>>(b, smem_cap);
         } else if (c->threads_per_source >= 512) {
             CUDA_TRY(cudaFuncSetAttribute(ali_march_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             ali_march_kernel<512><<<n_src, 512, smem, s>>>(b, smem_cap);

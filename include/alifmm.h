@@ -84,8 +84,9 @@ void alifmm_destroy(alifmm_ctx *ctx);
  * 0.4 already moves homogeneous-medium edge sources by 1e-4 and 0.5 changes the solution), "handover_margin" (nodes the sequential replica runs past the last
  * refined source box, default 27), "band_capacity_factor" (narrow-band list capacity as
  * a multiple of nz+nx of the solved grid, default 6), "threads_per_source" (CTA size of
- * the band march: 256, 512 or 1024, default 1024), "band_smem_kb" (shared memory for the
- * band lists, default 0 = keep L1 for the field gathers), "resort_every" (re-order the band
+ * the band march: 256, 512, 640, 768, 896 or 1024; default 768 = 80 registers per thread, measured
+ * fastest on B200), "band_smem_kb" (shared memory for the band lists, 0..180, default 0 = keep L1
+ * for the field gathers), "resort_every" (re-order the band
  * list along the front every this many rounds so that warps coalesce, default 8; 0 = never). */
 int alifmm_set_option(alifmm_ctx *ctx, const char *name, double value);
 

@@ -16,7 +16,7 @@ ap.add_argument("--sg", type=int, default=9)
 ap.add_argument("--nsrc", type=int, default=8)
 ap.add_argument("--frac", type=float, default=0.25)
 ap.add_argument("--margin", type=int, default=27)
-ap.add_argument("--threads", type=int, default=1024)
+ap.add_argument("--threads", type=int, default=768)
 ap.add_argument("--check", type=int, default=1, help="number of fields compared with the oracle")
 ap.add_argument("--rays", type=int, default=0)
 ap.add_argument("--reps", type=int, default=1)
