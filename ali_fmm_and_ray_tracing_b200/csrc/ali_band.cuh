@@ -121,13 +121,13 @@ ALI_DEV_NOINLINE double ali_band_fouds_slow(const AliModel *m_dev, const AliBand
 
 // Phase A: value the reference would store for this node given the current state.
 ALI_DEV double ali_band_eval(const AliModel &m, const AliModel *m_dev, const AliBandGrid &g,
-                             const AliBandGrid *g_mem, int iz, int ix, int *fallback)
+                             const AliBandGrid *g_mem, int iz, int ix, int *fallback, const double *sincos_tab = nullptr)
 {
     AliMat mat;
     AliWindow w;
     ali_fetch_mat(m, g.mv, iz, ix, mat);
     ali_band_gather(g, iz, ix, w);
-    double v = ali_update_window(m, mat, w, iz, ix, g.nz, g.nx, g.dnx, nullptr);
+    double v = ali_update_window(m, mat, w, iz, ix, g.nz, g.nx, g.dnx, nullptr, sincos_tab);
     if (v == -1.0) {
         v = ali_band_fouds_slow(m_dev, g_mem, iz, ix);
         *fallback = 1;

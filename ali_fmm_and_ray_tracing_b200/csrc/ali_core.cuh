@@ -78,7 +78,6 @@ struct AliModel {
     int has_stif;            // reference's "stif_den is not None"
     const double *group_tab; // [361*ncol]
     const double *phase_tab; // [361*ncol]
-    const double *sincos_tab; // nullptr, or a copy of ali_cr_sincos_tab in faster memory (set by the band march)
     int ncol;
     double dnx;
 };
@@ -226,10 +225,10 @@ ALI_DEV double ali_christoffel_group(double eff, const double *s, double vm)
     return 1000 * vm * sqrt(lam / s[4]) / ALI_COS(ALI_DEG2RAD * eff - ph);
 }
 
-ALI_DEV double ali_phase_velocity(const AliModel &m, const AliMat &mat, double eff)
+ALI_DEV double ali_phase_velocity(const AliModel &m, const AliMat &mat, double eff, const double *sincos_tab = nullptr)
 {
     if (mat.velpn != 0 || !m.has_stif) return ali_table_vel(m.phase_tab, m.ncol, eff, mat.velpn, mat.vel_map);
-    return ali_christoffel_phase(eff, mat.s, mat.vel_map, m.sincos_tab);
+    return ali_christoffel_phase(eff, mat.s, mat.vel_map, sincos_tab);
 }
 
 ALI_DEV double ali_group_velocity(const AliModel &m, const AliMat &mat, double eff)
@@ -282,7 +281,7 @@ struct AliWindow {
 //   returns -1.0 when no stencil gives a solution (caller falls back to fouds18).
 // The window is indexed with compile-time slots only, so it lives in registers.
 ALI_DEV double ali_update_window(const AliModel &m, const AliMat &mat, const AliWindow &w, int iz, int ix,
-                                 int nnz, int nnx, double dnx, int *stencil_out)
+                                 int nnz, int nnx, double dnx, int *stencil_out, const double *sincos_tab = nullptr)
 {
     const unsigned av = w.avail;
     int stencil_no = -1;
@@ -377,7 +376,7 @@ ALI_DEV double ali_update_window(const AliModel &m, const AliMat &mat, const Ali
     if (stencil_out) *stencil_out = stencil_no;
     if (dist != -1.0) {
         double eff = ali_pymod180(mat.veln - angle);
-        double vel = ali_phase_velocity(m, mat, eff);
+        double vel = ali_phase_velocity(m, mat, eff, sincos_tab);   // sincos_tab: optional copy of the sin/cos table in faster memory
         return wt + (dist * dnx / vel);
     }
     return -1.0;

@@ -283,8 +283,6 @@ __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
     }
 
     for (int q = tid; q < 404 * 4; q += NT) s_sincos[q] = ali_cr_sincos_tab[q];
-    AliModel mdl = b.m;
-    mdl.sincos_tab = s_sincos;
     if (tid == 0) {
         s_grid = g;
         s_count[0] = 0; s_count[1] = 0; s_nwork[0] = 0; s_nwork[1] = 0;
@@ -360,7 +358,7 @@ __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
             const int iz = ALI_PACK_Z(e), ix = ALI_PACK_X(e);
             int fb = 0;
             const double vold = val[i];   // the value this node last published (0: none yet)
-            const double v = ali_band_eval(mdl, b.m_dev, g, &s_grid, iz, ix, &fb);
+            const double v = ali_band_eval(b.m, b.m_dev, g, &s_grid, iz, ix, &fb, s_sincos);
             val[i] = v;
             my_evals++;
             my_fbs += fb;

@@ -62,7 +62,6 @@ static void make_model(HostModel &h, int nz, int nx, const double *veln, const i
     AliModel &m = h.m;
     m.nz = nz; m.nx = nx; m.rec = h.rec.data();
     m.has_stif = has_stif; m.group_tab = group_tab; m.phase_tab = phase_tab; m.ncol = ncol; m.dnx = dnx;
-    m.sincos_tab = nullptr;
 }
 
 
