@@ -78,6 +78,24 @@ class _Bar:
             self.bar.close()
 
 
+def _zeros_sparse(shape):
+    """np.zeros for a large array of which only a small part will be written (the dense ray-path
+    arrays: 2 x 605 MB for 128 transducers, ~6 % used).  With transparent huge pages set to
+    "always" the first touch of every 2 MB region zeroes all of it (0.1 s per call for the
+    headline workload); an anonymous mapping that opts out of huge pages only pays for the 4 KB
+    pages that are written."""
+    import mmap
+    n = int(np.prod(shape)) * 8
+    if n < (64 << 20) or not hasattr(mmap, "MADV_NOHUGEPAGE"):
+        return np.zeros(shape)
+    mm = mmap.mmap(-1, n)
+    try:
+        mm.madvise(mmap.MADV_NOHUGEPAGE)
+    except (OSError, ValueError):
+        pass
+    return np.frombuffer(mm, dtype=np.float64).reshape(shape)
+
+
 def _split(items, parts):
     """Contiguous, balanced partition of ``items`` into ``parts`` lists."""
     k, r = divmod(len(items), parts)
@@ -422,8 +440,8 @@ class ALI_FMM:
         n_trans = len(self.isx)
         cap = 5 * (veln.shape[0] + veln.shape[1])
         if save_rays:
-            self.ray_paths_x = np.zeros((n_trans, n_trans, cap))
-            self.ray_paths_y = np.zeros((n_trans, n_trans, cap))
+            self.ray_paths_x = _zeros_sparse((n_trans, n_trans, cap))
+            self.ray_paths_y = _zeros_sparse((n_trans, n_trans, cap))
             self.ray_len = np.zeros((n_trans, n_trans), dtype=int)
         self.ray_flags = np.zeros((n_trans, n_trans), dtype=int)
         if type(trans_pairs) == type(None):
