@@ -19,6 +19,7 @@
 #include <string>
 #include <vector>
 #include <mutex>
+#include <thread>
 
 #include "../../include/alifmm.h"
 #include "ali_core.cuh"
@@ -1338,10 +1339,23 @@ extern "C" int alifmm_rays_into(alifmm_ctx *c, int32_t n_rays, const int32_t *sr
             pin_give(pin, pin_bytes);
             return fail(ALIFMM_E_CUDA, std::string("alifmm_rays_into: ") + cudaGetErrorString(e));
         }
-        for (int r = 0; r < n_rays; r++) {
-            const size_t n = (size_t)out_len[r];
-            memcpy(base_x + (size_t)row[r] * cap, pin + off[r], n * sizeof(double));
-            memcpy(base_y + (size_t)row[r] * cap, pin + total + off[r], n * sizeof(double));
+        // scatter into the caller's rows; mostly first-touch page faults of a fresh destination, so a few
+        // host threads share it
+        {
+            unsigned nt = std::thread::hardware_concurrency();
+            nt = nt < 1 ? 1 : (nt > 8 ? 8 : nt);
+            if (n_rays < 256) nt = 1;
+            auto work = [&](int t) {
+                for (int r = t; r < n_rays; r += (int)nt) {
+                    const size_t n = (size_t)out_len[r];
+                    memcpy(base_x + (size_t)row[r] * cap, pin + off[r], n * sizeof(double));
+                    memcpy(base_y + (size_t)row[r] * cap, pin + total + off[r], n * sizeof(double));
+                }
+            };
+            std::vector<std::thread> th;
+            for (unsigned t = 1; t < nt; t++) th.emplace_back(work, (int)t);
+            work(0);
+            for (auto &x : th) x.join();
         }
         pin_give(pin, pin_bytes);
     }
