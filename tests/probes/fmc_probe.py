@@ -1,6 +1,6 @@
 """Dev probe: FMC all-pairs on the weld at subgrid 3 against the oracle (times and path distances)."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from tests import models
 from oracle import ali_oracle as orc

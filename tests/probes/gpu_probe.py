@@ -3,7 +3,7 @@ import argparse
 import sys
 import time
 import os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from ali_fmm_and_ray_tracing_b200 import build as _b
 if os.environ.get("ALIFMM_LIB"):

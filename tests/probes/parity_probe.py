@@ -1,6 +1,6 @@
 """Dev probe: GPU fields vs the oracle (glibc) and vs the host replay run on the device's math (bit-exactness)."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from ali_fmm_and_ray_tracing_b200 import _capi
 from tests import models

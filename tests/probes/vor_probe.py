@@ -1,6 +1,6 @@
 """Dev probe: Voronoi 768 lattice sources, GPU vs oracle, optional library override / options."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from ali_fmm_and_ray_tracing_b200 import build as _b
 if os.environ.get("ALIFMM_LIB"):
