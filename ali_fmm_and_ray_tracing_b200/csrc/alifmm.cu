@@ -832,6 +832,88 @@ static int dev_reserve(DevBuf &b, size_t bytes)
 
 static void dev_release(DevBuf &b, int device) { dev_give_back(b, device); }
 
+// Pinned staging buffers are recycled like the device buffers (cudaHostAlloc costs tens of ms).
+static std::vector<PoolEntry> g_pin_pool;
+static void *pin_take(size_t bytes, size_t *got)
+{
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mutex);
+        for (size_t i = 0; i < g_pin_pool.size(); i++)
+            if (g_pin_pool[i].bytes >= bytes) {
+                void *p = g_pin_pool[i].p;
+                *got = g_pin_pool[i].bytes;
+                g_pin_pool[i] = g_pin_pool.back();
+                g_pin_pool.pop_back();
+                return p;
+            }
+    }
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    *got = bytes;
+    return p;
+}
+static void pin_give(void *p, size_t bytes)
+{
+    std::lock_guard<std::mutex> lk(g_pool_mutex);
+    g_pin_pool.push_back(PoolEntry{p, bytes, -1});
+}
+
+// Field results -> caller's (pageable) memory.  A plain cudaMemcpy into pageable memory runs at
+// ~5 GB/s (the driver stages it, and a fresh destination takes a page fault per 4 KB); here the
+// copy is pipelined through two pinned buffers and the host side of it is shared by a few threads.
+static int copy_to_host(alifmm_ctx *c, void *dst, const void *src_dev, size_t bytes)
+{
+    cudaStream_t s = c->stream;
+    const size_t CH = (size_t)64 << 20;
+    size_t g0 = 0, g1 = 0;
+    char *pin[2] = {nullptr, nullptr};
+    if (bytes >= ((size_t)16 << 20)) {
+        pin[0] = (char *)pin_take(CH, &g0);
+        pin[1] = pin[0] ? (char *)pin_take(CH, &g1) : nullptr;
+    }
+    if (!pin[0] || !pin[1]) {
+        if (pin[0]) pin_give(pin[0], g0);
+        CUDA_TRY(cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        return ALIFMM_OK;
+    }
+    cudaEvent_t ev[2];
+    cudaError_t e = cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
+    const size_t nch = (bytes + CH - 1) / CH;
+    auto issue = [&](size_t i) -> cudaError_t {
+        const size_t off = i * CH, n = bytes - off < CH ? bytes - off : CH;
+        cudaError_t r = cudaMemcpyAsync(pin[i & 1], (const char *)src_dev + off, n, cudaMemcpyDeviceToHost, s);
+        if (r == cudaSuccess) r = cudaEventRecord(ev[i & 1], s);
+        return r;
+    };
+    unsigned nt = std::thread::hardware_concurrency();
+    nt = nt < 1 ? 1 : (nt > 8 ? 8 : nt);
+    if (e == cudaSuccess) e = issue(0);
+    for (size_t i = 0; i < nch && e == cudaSuccess; i++) {
+        if (i + 1 < nch) e = issue(i + 1);          // the other buffer was consumed in the previous iteration
+        if (e == cudaSuccess) e = cudaEventSynchronize(ev[i & 1]);
+        if (e != cudaSuccess) break;
+        const size_t off = i * CH, n = bytes - off < CH ? bytes - off : CH;
+        const size_t part = ((n / nt) + 4095) & ~(size_t)4095;
+        auto work = [&](unsigned t) {
+            const size_t a = (size_t)t * part;
+            if (a >= n) return;
+            const size_t m = n - a < part ? n - a : part;
+            memcpy((char *)dst + off + a, pin[i & 1] + a, m);
+        };
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < nt; t++) th.emplace_back(work, t);
+        work(0);
+        for (auto &x : th) x.join();
+    }
+    if (e != cudaSuccess) cudaStreamSynchronize(s);
+    cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
+    pin_give(pin[0], g0); pin_give(pin[1], g1);
+    if (e != cudaSuccess) return fail(ALIFMM_E_CUDA, std::string("copy_to_host: ") + cudaGetErrorString(e));
+    return ALIFMM_OK;
+}
+
 template <class Tp>
 static int upload(alifmm_ctx *c, const Tp *host, size_t n, const Tp **dev_out)
 {
@@ -1106,8 +1188,6 @@ static int ttf_attempt(alifmm_ctx *c, int32_t n_src, const int32_t *src_iz, cons
     }
     CUDA_TRY(cudaEventRecord(c->ev[3], s));
     CUDA_TRY(cudaMemcpyAsync(recs.data(), b.rec, recs.size() * sizeof(AliSourceRec), cudaMemcpyDeviceToHost, s));
-    if (out_host)
-        CUDA_TRY(cudaMemcpyAsync(out_host, b.T, (size_t)n_src * N * sizeof(double), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
 
     alifmm_counters_t &cn = c->cnt;
@@ -1159,6 +1239,7 @@ static int ttf_attempt(alifmm_ctx *c, int32_t n_src, const int32_t *src_iz, cons
     if (overflow & 1)
         return fail(ALIFMM_E_CAPACITY, "alifmm_ttf: sequential near-source scratch overflowed");
     c->n_slots = n_src; c->sg = sg; c->fz = fz; c->fx = fx;
+    if (out_host) return copy_to_host(c, out_host, b.T, (size_t)n_src * N * sizeof(double));
     return ALIFMM_OK;
 }
 
@@ -1178,10 +1259,7 @@ extern "C" int alifmm_ttf_fetch(alifmm_ctx *c, int32_t slot, double *out_host)
     if (slot < 0 || slot >= c->n_slots) return fail(ALIFMM_E_STATE, "alifmm_ttf_fetch: no such resident field");
     CUDA_TRY(cudaSetDevice(c->device));
     const size_t N = (size_t)c->fz * c->fx;
-    CUDA_TRY(cudaMemcpyAsync(out_host, (double *)c->T.p + (size_t)slot * N, N * sizeof(double),
-                             cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    return ALIFMM_OK;
+    return copy_to_host(c, out_host, (double *)c->T.p + (size_t)slot * N, N * sizeof(double));
 }
 
 // Validates the jobs, launches the ray kernel and leaves its outputs in the context's device buffers.
@@ -1271,32 +1349,6 @@ __global__ void ali_ray_pack_kernel(const double *x, const double *y, const int 
         dx[k] = sx[k] / divisor;
         dy[k] = sy[k] / divisor;
     }
-}
-
-// Pinned staging buffers are recycled like the device buffers (cudaHostAlloc costs tens of ms).
-static std::vector<PoolEntry> g_pin_pool;
-static void *pin_take(size_t bytes, size_t *got)
-{
-    {
-        std::lock_guard<std::mutex> lk(g_pool_mutex);
-        for (size_t i = 0; i < g_pin_pool.size(); i++)
-            if (g_pin_pool[i].bytes >= bytes) {
-                void *p = g_pin_pool[i].p;
-                *got = g_pin_pool[i].bytes;
-                g_pin_pool[i] = g_pin_pool.back();
-                g_pin_pool.pop_back();
-                return p;
-            }
-    }
-    void *p = nullptr;
-    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    *got = bytes;
-    return p;
-}
-static void pin_give(void *p, size_t bytes)
-{
-    std::lock_guard<std::mutex> lk(g_pool_mutex);
-    g_pin_pool.push_back(PoolEntry{p, bytes, -1});
 }
 
 extern "C" int alifmm_rays_into(alifmm_ctx *c, int32_t n_rays, const int32_t *src_iz, const int32_t *src_ix,
