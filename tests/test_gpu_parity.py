@@ -495,6 +495,43 @@ def test_weld_sg9_rays_against_reference(capi):
     assert good >= 3
 
 
+def test_weld_rays_py_script_workflow(capi, tmp_path):
+    """BASELINE config 2: the reference's own driver script (Weld_rays.py:38-72) on the drop-in class
+    -- 31 + 31 transducers, find_all_TTF_rays_parallel at the default subgrid 9 (31 receiver fields of
+    17.1 M nodes, 961 rays), the max_len slicing and the four .npy files plot_rays.py reads back."""
+    from Anis_TTF_rays import ALI_FMM
+    w = models.weld()
+    scx, scz, pairs = models.weld_rays_py()
+    fm = ALI_FMM(w["veln"], w["velpn"], w["vel_map"], scx, scz, stif_den=w["stif_den"], dnx=w["dnx"])
+    trav_times = fm.find_all_TTF_rays_parallel(w["veln"], w["velpn"], w["vel_map"], stif_den=w["stif_den"], n_threads=8,
+                                               trans_pairs=pairs)
+    assert trav_times.shape == (62, 62) and (trav_times > 0).sum() == 961
+    assert not trav_times[31:, :].any() and not trav_times[:, :31].any()
+    assert (fm.ray_len > 0).sum() == 961 and fm.ray_paths_x.shape == (62, 62, 5 * (424 + 500))
+    max_len = np.max(fm.ray_len)
+    assert 800 < max_len < 1200
+    rx, ry = fm.ray_paths_x[:, :, 0:max_len], fm.ray_paths_y[:, :, 0:max_len]
+    for name, arr in (("trav_times", trav_times), ("ray_paths_x", rx), ("ray_paths_y", ry), ("ray_len", fm.ray_len)):
+        np.save(tmp_path / (name + ".npy"), arr)
+        assert np.array_equal(np.load(tmp_path / (name + ".npy")), arr)
+    # every path starts on its source, ends on its receiver and stays inside the plate
+    for i in range(31):
+        for j in (31, 40, 61):
+            n = fm.ray_len[i, j]
+            assert (rx[i, j, 0], ry[i, j, 0]) == (fm.isx[i], fm.isz[i]) and (rx[i, j, n - 1], ry[i, j, n - 1]) == (fm.isx[j], fm.isz[j])
+            assert rx[i, j, :n].min() >= 0 and rx[i, j, :n].max() <= 499 and ry[i, j, :n].min() >= 0 and ry[i, j, :n].max() <= 423
+            assert not rx[i, j, n:].any()
+    # the rays the reference itself produced for receiver 40 (tests/golden/make_golden.py)
+    gold = _load("golden_rays.npz")
+    good = 0
+    for k, sx in enumerate(gold["weld9_ray_srcx"]):
+        i = int(round((sx - 25) / 15))
+        x, y = fm.ray_path(i, 40)
+        assert abs(trav_times[i, 40] - gold["weld9_ray_times"][k]) <= 1e-4 * gold["weld9_ray_times"][k]
+        good += models.polyline_distance(x, y, gold["weld9_ray_x_%d" % k], gold["weld9_ray_y_%d" % k]) <= TOL_CELL
+    assert good >= 3
+
+
 # ----------------------------------------------------------------------------- reference-facing API
 def test_class_api_shapes_and_conventions(capi, tmp_path, monkeypatch):
     from Anis_TTF_rays import ALI_FMM
