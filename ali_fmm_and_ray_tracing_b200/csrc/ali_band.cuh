@@ -125,7 +125,7 @@ ALI_DEV double ali_band_eval(const AliModel &m, const AliModel *m_dev, const Ali
 {
     AliMat mat;
     AliWindow w;
-    ali_fetch_mat(m, g.mv, iz, ix, mat);
+    ali_fetch_mat_refined(m, g.mv.scale0, g.mv.side0, g.mv.mul0, g.mv.cast, iz, ix, mat);   // g.mv is ali_band_view(sg)
     ali_band_gather(g, iz, ix, w);
     double v = ali_update_window(m, mat, w, iz, ix, g.nz, g.nx, g.dnx, nullptr, sincos_tab);
     if (v == -1.0) {

@@ -149,6 +149,30 @@ ALI_DEV void ali_fetch_mat(const AliModel &m, const AliMatView &v, int iz, int i
     out.s = r->s;
 }
 
+// The same fetch for a grid that is the coarse model refined by `scale0` only (the band march's view:
+// no level, no origin), so that the hot loop keeps four values of the view instead of nine.
+ALI_DEV void ali_fetch_mat_refined(const AliModel &m, int scale0, int side0, unsigned mul0, int cast, int iz, int ix,
+                                   AliMat &out)
+{
+    const int cz = ali_div_by(iz + side0, scale0, mul0);
+    const int cx = ali_div_by(ix + side0, scale0, mul0);
+    const AliMatRec *r = m.rec + ((size_t)cz * (size_t)m.nx + (size_t)cx);
+#if defined(__CUDA_ARCH__)
+    const double2 vv = __ldg(reinterpret_cast<const double2 *>(r));
+    double vn = vv.x, vm = vv.y;
+#else
+    double vn = r->veln, vm = r->vel_map;
+#endif
+    if (cast) {
+        vn = (double)(int)vn;
+        vm = (double)(float)vm;
+    }
+    out.veln = vn;
+    out.vel_map = vm;
+    out.velpn = r->velpn;
+    out.s = r->s;
+}
+
 ALI_DEV int ali_imax2(int a, int b) { return a > b ? a : b; }
 ALI_DEV int ali_imin2(int a, int b) { return a < b ? a : b; }
 

@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
     __shared__ int s_bins[ALI_SORT_BINS];
     __shared__ int s_wsum[32];
     __shared__ int s_force[2];   // by round parity: re-evaluate the whole band (FD fallback outside the register path)
-    long long cyc[4] = {0, 0, 0, 0};
+    __shared__ long long s_cyc[4], s_tprev;   // phase timing, kept by thread 0 in shared memory (no registers in the hot loop)
     const int isz = (b.sg > 1 ? b.sg : 1) * rec.src_iz, isx = (b.sg > 1 ? b.sg : 1) * rec.src_ix;
 
     AliBandGrid g;
@@ -291,6 +291,7 @@ __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
         s_overflow = rec.overflow;
         s_evals = 0; s_fbs = 0;
         s_force[0] = 0; s_force[1] = 0;
+        s_cyc[0] = s_cyc[1] = s_cyc[2] = s_cyc[3] = 0;
     }
     __syncthreads();
     if (s_overflow) return;
@@ -331,8 +332,8 @@ __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
     if (tid == 0) s_nwork[0] = s_count[0];
     __syncthreads();
 
-    long long rounds = 0, max_band = 0;
-    unsigned long long my_evals = 0, my_fbs = 0;
+    int rounds = 0, max_band = 0;
+    unsigned my_evals = 0, my_fbs = 0;   // per thread: a field has fewer than 2^31 nodes
     int cur = 0;
     while (true) {
         const int n = s_count[cur];
@@ -343,7 +344,7 @@ __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
         unsigned *wrk = cur == 0 ? wrk0 : wrk1, *nwrk = cur == 0 ? wrk1 : wrk0;
         rounds++;
         if (n > max_band) max_band = n;
-        long long t0 = clock64();
+        if (tid == 0) s_tprev = clock64();
         // phase A: evaluate the work list from the round's snapshot.  The first two items of a thread
         // stay in registers for phase B (a round rarely has more than 2 * NT items); the minimum of
         // the new values is reduced here so that phase B has nothing to wait for.
@@ -376,7 +377,7 @@ __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
         if ((tid & 31) == 0 && lmin < 1e300)
             atomicMin(&s_evalmin[cur], (unsigned long long)__double_as_longlong(lmin));
         __syncthreads();
-        long long t1 = clock64();
+        if (tid == 0) { const long long now = clock64(); s_cyc[0] += now - s_tprev; s_tprev = now; }
         // phase B: publish the re-evaluated values that changed and mark their window neighbours.
         // A node the FD fallback evaluated also depends on alive flags: it is re-evaluated every
         // round (its own bit), like the reference re-evaluates it on every neighbouring pop.
@@ -396,7 +397,7 @@ __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
             }
         }
         __syncthreads();
-        long long t2 = clock64();
+        if (tid == 0) { const long long now = clock64(); s_cyc[1] += now - s_tprev; s_tprev = now; }
         // phase C: accept + extend the band; compact survivors; next work list (deferred to the
         // re-sort pass on the rounds that re-order the list along the front)
         const bool resort = b.resort_every > 0 && (rounds % b.resort_every) == 0;
@@ -443,7 +444,7 @@ __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
         if ((tid & 31) == 0 && bmin < 1e300)
             atomicMin(&s_basemin[cur ^ 1], (unsigned long long)__double_as_longlong(bmin));
         __syncthreads();
-        long long t3 = clock64();
+        if (tid == 0) { const long long now = clock64(); s_cyc[2] += now - s_tprev; s_tprev = now; }
         if (resort && s_count[cur ^ 1] > 64 && !s_overflow) {
             // counting sort of the new list by angular bin, from the "next" buffers back into the
             // current ones (free now); then the work list / base minimum on the sorted order
@@ -523,19 +524,18 @@ __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
             cur ^= 1;
         }
         if (tid == 0) {
-            long long t4 = clock64();
-            cyc[0] += t1 - t0; cyc[1] += t2 - t1; cyc[2] += t3 - t2; cyc[3] += t4 - t3;
+            const long long now = clock64(); s_cyc[3] += now - s_tprev;
         }
     }
-    atomicAdd(&s_evals, my_evals);
-    atomicAdd(&s_fbs, my_fbs);
+    atomicAdd(&s_evals, (unsigned long long)my_evals);
+    atomicAdd(&s_fbs, (unsigned long long)my_fbs);
     __syncthreads();
     if (tid == 0) {
         rec.rounds = rounds;
         rec.max_band = max_band;
         rec.band_evals = (long long)s_evals;
         rec.band_fallbacks = (long long)s_fbs;
-        for (int q = 0; q < 4; q++) rec.cycles[q] = cyc[q];
+        for (int q = 0; q < 4; q++) rec.cycles[q] = s_cyc[q];
         if (s_overflow) rec.overflow = s_overflow;
     }
 }
