@@ -732,7 +732,7 @@ struct alifmm_ctx {
     const AliModel *m_dev = nullptr;
     int first_velpn = 0;
     int nz = 0, nx = 0;
-    std::vector<void *> model_allocs;
+    std::vector<DevBuf> model_allocs;   // pooled like the batch buffers (cudaFree stalls for up to 0.8 s now and then)
     double vmax = 0.0;
     // options
     double delta_frac = 0.3;
@@ -750,7 +750,7 @@ struct alifmm_ctx {
 // Large device buffers are recycled through a per-device pool: the reference-facing API creates a
 // context per call (it re-takes the model every time, ATR:3889-3900), and cudaFree / cudaMalloc of
 // the tens of GB a headline batch needs cost 0.7 s per call otherwise.  alifmm_trim() empties it.
-#define ALI_POOL_MIN_BYTES ((size_t)1 << 20)
+#define ALI_POOL_MIN_BYTES ((size_t)4096)
 struct PoolEntry { void *p; size_t bytes; int device; };
 static std::mutex g_pool_mutex;
 static std::vector<PoolEntry> g_pool;
@@ -805,7 +805,7 @@ static int dev_reserve(DevBuf &b, size_t bytes)
         std::lock_guard<std::mutex> lk(g_pool_mutex);
         int best = -1;
         for (size_t i = 0; i < g_pool.size(); i++)
-            if (g_pool[i].device == device && g_pool[i].bytes >= bytes && g_pool[i].bytes <= bytes + bytes / 4 + (64 << 20) &&
+            if (g_pool[i].device == device && g_pool[i].bytes >= bytes && g_pool[i].bytes <= bytes + bytes / 4 + (1 << 20) &&
                 (best < 0 || g_pool[i].bytes < g_pool[best].bytes))
                 best = (int)i;
         if (best >= 0) {
@@ -917,11 +917,12 @@ static int copy_to_host(alifmm_ctx *c, void *dst, const void *src_dev, size_t by
 template <class Tp>
 static int upload(alifmm_ctx *c, const Tp *host, size_t n, const Tp **dev_out)
 {
-    void *d = nullptr;
-    CUDA_TRY(cudaMalloc(&d, n * sizeof(Tp)));
-    c->model_allocs.push_back(d);
-    CUDA_TRY(cudaMemcpyAsync(d, host, n * sizeof(Tp), cudaMemcpyHostToDevice, c->stream));
-    *dev_out = (const Tp *)d;
+    DevBuf buf;
+    int rc = dev_reserve(buf, n * sizeof(Tp));
+    if (rc != ALIFMM_OK) return rc;
+    c->model_allocs.push_back(buf);
+    CUDA_TRY(cudaMemcpyAsync(buf.p, host, n * sizeof(Tp), cudaMemcpyHostToDevice, c->stream));
+    *dev_out = (const Tp *)buf.p;
     return ALIFMM_OK;
 }
 
@@ -939,7 +940,7 @@ extern "C" void alifmm_destroy(alifmm_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    for (void *p : c->model_allocs) cudaFree(p);
+    for (DevBuf &mb : c->model_allocs) dev_release(mb, c->device);
     DevBuf *bufs[] = {&c->T, &c->Tt, &c->st, &c->seq_t, &c->seq_s, &c->seq_heap, &c->seq_hkey, &c->seq_cval, &c->seq_cflag, &c->lists, &c->stage, &c->rec, &c->jobs,
                       &c->ray_x, &c->ray_y, &c->ray_time, &c->ray_len, &c->ray_flag, &c->ray_off, &c->pack, &c->misc};
     for (DevBuf *b : bufs) dev_release(*b, c->device);
@@ -988,28 +989,28 @@ extern "C" int alifmm_create(const alifmm_model_desc *d, int device, alifmm_ctx 
         if ((rc = upload(c, d->velpn, n, &dp)) != 0) return bail(rc);
         if ((rc = upload(c, d->vel_map, n, &dm)) != 0) return bail(rc);
         if (d->stif_den && (rc = upload(c, (const long long *)d->stif_den, n * 5, &ds)) != 0) return bail(rc);
-        void *recp = nullptr;
-        if (cudaMalloc(&recp, n * sizeof(AliMatRec)) != cudaSuccess)
-            return bail(fail(ALIFMM_E_CUDA, "alifmm_create: cudaMalloc(records) failed"));
+        DevBuf recb;
+        if ((rc = dev_reserve(recb, n * sizeof(AliMatRec))) != 0) return bail(rc);
+        void *recp = recb.p;
         int blocks = (int)((n + 255) / 256);
         if (blocks > 148 * 8) blocks = 148 * 8;
         ali_records_kernel<<<blocks, 256, 0, c->stream>>>((int)n, dv, dp, dm, ds, (AliMatRec *)recp);
         if (cudaStreamSynchronize(c->stream) != cudaSuccess) {
-            cudaFree(recp);
+            dev_release(recb, c->device);
             return bail(fail(ALIFMM_E_CUDA, std::string("alifmm_create: records kernel failed: ") + cudaGetErrorString(cudaGetLastError())));
         }
-        for (void *q : c->model_allocs) cudaFree(q);
+        for (DevBuf &q : c->model_allocs) dev_release(q, c->device);
         c->model_allocs.clear();
-        c->model_allocs.push_back(recp);
+        c->model_allocs.push_back(recb);
         c->m.rec = (const AliMatRec *)recp;
     }
     if ((rc = upload(c, d->group_vel, (size_t)361 * d->n_cols, &c->m.group_tab)) != 0) return bail(rc);
     if ((rc = upload(c, d->phase_vel, (size_t)361 * d->n_cols, &c->m.phase_tab)) != 0) return bail(rc);
     {   // the model struct itself, in device memory, for out-of-line slow paths
-        void *mp = nullptr;
-        if (cudaMalloc(&mp, sizeof(AliModel)) != cudaSuccess)
-            return bail(fail(ALIFMM_E_CUDA, "alifmm_create: cudaMalloc(model) failed"));
-        c->model_allocs.push_back(mp);
+        DevBuf mb;
+        if ((rc = dev_reserve(mb, sizeof(AliModel) < 4096 ? 4096 : sizeof(AliModel))) != 0) return bail(rc);
+        void *mp = mb.p;
+        c->model_allocs.push_back(mb);
         if (cudaMemcpyAsync(mp, &c->m, sizeof(AliModel), cudaMemcpyHostToDevice, c->stream) != cudaSuccess)
             return bail(fail(ALIFMM_E_CUDA, "alifmm_create: model upload failed"));
         c->m_dev = (const AliModel *)mp;

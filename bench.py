@@ -262,9 +262,12 @@ def run_gpu(args):
                                   stif_den=w["stif_den"], n_threads=8)   # warm-up (allocations, page faults)
     barrier()
     t0 = time.perf_counter()
+    e2e_calls = []
     for _ in range(e2e_steps):
+        tc = time.perf_counter()
         times = fm.find_all_TTF_rays_parallel(w["veln"], w["velpn"], w["vel_map"], subgrid_size=SG, trans_pairs=pairs,
                                               stif_den=w["stif_den"], n_threads=8)
+        e2e_calls.append(time.perf_counter() - tc)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
@@ -321,7 +324,8 @@ def run_gpu(args):
                          "note": "the march is round-latency bound (one barrier-separated round per 0.3 dnx/vmax of "
                                  "travel time), not bandwidth bound; see DESIGN.md"},
             "e2e": {"value": e2e_value, "unit": "node-solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "ALI_FMM.find_all_TTF_rays_parallel", "steps": e2e_steps, "s_per_step": e2e_s / e2e_steps},
+                    "api": "ALI_FMM.find_all_TTF_rays_parallel", "steps": e2e_steps, "s_per_step": e2e_s / e2e_steps,
+                    "s_per_call": [round(t, 4) for t in e2e_calls]},
             "gpu_launches": launches, "clocks": clocks,
         }
         if cpu is not None:
