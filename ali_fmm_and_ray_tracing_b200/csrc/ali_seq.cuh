@@ -346,13 +346,9 @@ ALI_DEV void ali_seq_invalidate(const AliSeqGrid &g, int z, int x, unsigned wi)
 // Speculation looks at the neighbours of the first ALI_COOP_HEAP_POSITIONS heap entries (the
 // likely next pops).  wanted(hp): 4-bit mask of the directions (x-1, x+1, z-1, z+1) whose node is
 // not alive and has no valid cached update.
-#ifndef ALI_COOP_HEAP_POSITIONS
-#if defined(ALI_COOP_RANKED)
-#define ALI_COOP_HEAP_POSITIONS 32   // candidates ranked by heap position with ballots / __fns: 3 % fewer steps, 35 % dearer
-#else
-#define ALI_COOP_HEAP_POSITIONS 8    // lane -> (heap position, direction), no ranking (measured faster on B200)
-#endif
-#endif
+// (Ranking the candidates of the first 32 entries with ballots / __fns was measured too: 3 % fewer
+// steps, each 35 % dearer.)
+#define ALI_COOP_HEAP_POSITIONS 8
 ALI_DEV unsigned ali_coop_wanted(const AliSeqGrid &g, int hp, int ntr)
 {
     unsigned mask = 0;
@@ -493,7 +489,6 @@ ALI_DEV int ali_seq_march_coop(AliSeqGrid &g_mem, const AliModel &m, int cx, int
                 has = ali_coop_wanted_node(g, cz_c, cx_c);
             }
         }
-#if !defined(ALI_COOP_RANKED)
         // fixed assignment: lane -> (heap position, direction) of the first 7-8 heap entries
         {
             const int slot = serve ? lane - 4 : lane;
@@ -507,37 +502,6 @@ ALI_DEV int ali_seq_march_coop(AliSeqGrid &g_mem, const AliModel &m, int cx, int
                 }
             }
         }
-#else
-        // candidates of heap positions 1..32 (4 bits each), packed 8 positions per word; the lanes take
-        // them in heap order
-        unsigned w4 = ali_coop_wanted(g, lane + 1, ntr) << (4 * (lane & 7));
-        w4 |= __shfl_xor_sync(0xffffffffu, w4, 1);
-        w4 |= __shfl_xor_sync(0xffffffffu, w4, 2);
-        w4 |= __shfl_xor_sync(0xffffffffu, w4, 4);
-        unsigned words[4];
-#pragma unroll
-        for (int q = 0; q < 4; q++) words[q] = __shfl_sync(0xffffffffu, w4, 8 * q);
-        int j = serve ? lane - 4 : lane;
-        if (j >= 0) {
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const int c = __popc(words[q]);
-                if (!has) {
-                    if (j < c) {
-                        const int bit = (int)__fns(words[q], 0, j + 1);
-                        const int hp = 8 * q + (bit >> 2) + 1, dir = bit & 3;
-                        const AliHeapEnt he = g.heap[hp];
-                        cz_c = ALI_ENT_Z(he) + (dir == 2 ? -1 : dir == 3 ? 1 : 0);
-                        cx_c = ALI_ENT_X(he) + (dir == 0 ? -1 : dir == 1 ? 1 : 0);
-                        has = true;
-                        j = -1000;
-                    } else {
-                        j -= c;
-                    }
-                }
-            }
-        }
-#endif
         const int did = ali_coop_step(g, m, cs, serve && lane == 0, has, cz_c, cx_c);
         const unsigned mask = __ballot_sync(0xffffffffu, did);
         if (lane == 0) {

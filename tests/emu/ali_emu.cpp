@@ -137,7 +137,7 @@ static void band_run(const AliModel &m, AliBandGrid &bg, std::vector<unsigned> &
             if (bg.dirty[di] || eager) {
                 int fb = 0;
                 bg.dirty[di] = 0;
-                tnew[i] = ali_band_eval(m, &m, bg, &bg, iz, ix, &fb);
+                tnew[i] = ali_band_eval(m, &m, bg, &bg, iz, ix, &fb, nullptr, stop_mask != 0);
                 if (fb) bg.dirty[di] = 1;
                 st.evals++; st.fbs += fb;
             } else {
