@@ -132,3 +132,25 @@ def test_world_size_2_sharding_over_gloo():
         p.join(timeout=120)
         assert p.exitcode == 0
     assert merged == [0] * 7 + [1] * 6 and total == 13.0 and tmax == 2.0
+
+
+def test_dense_ray_arrays_behave_like_numpy_zeros():
+    """The class allocates ray_paths_x / ray_paths_y (mostly empty, hundreds of MB) from a mapping
+    that opts out of transparent huge pages; callers must not notice (Weld_rays.py slices and saves them)."""
+    import io
+    from ali_fmm_and_ray_tracing_b200.Anis_TTF_rays import _zeros_sparse
+    small = _zeros_sparse((3, 3, 10))
+    big = _zeros_sparse((40, 40, 6000))           # 76.8 MB: the mapped path
+    for a in (small, big):
+        assert isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous and a.flags.writeable
+        assert not a.any()
+    big[1, 2, :5] = np.arange(5)
+    view = big[:, :, 0:7]
+    buf = io.BytesIO()
+    np.save(buf, view)
+    buf.seek(0)
+    back = np.load(buf)
+    assert back.shape == (40, 40, 7) and np.array_equal(back[1, 2, :5], np.arange(5)) and back.sum() == 10
+    copy = big.copy()
+    del big, view                                  # the mapping goes away with the last reference
+    assert copy[1, 2, 4] == 4.0
