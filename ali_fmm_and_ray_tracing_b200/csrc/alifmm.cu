@@ -1265,7 +1265,7 @@ extern "C" int alifmm_ttf_fetch(alifmm_ctx *c, int32_t slot, double *out_host)
 
 // Validates the jobs, launches the ray kernel and leaves its outputs in the context's device buffers.
 static int rays_launch(alifmm_ctx *c, int32_t n_rays, const int32_t *src_iz, const int32_t *src_ix,
-                       const int32_t *rec_slot, int32_t cap, AliRayArgs &a)
+                       const int32_t *rec_slot, int32_t cap, AliRayArgs &a, bool zero_paths = false)
 {
     if (c->n_slots < 1) return fail(ALIFMM_E_STATE, "alifmm_rays: no resident travel-time fields (call alifmm_ttf first)");
     if (n_rays < 1) return fail(ALIFMM_E_INVALID, "alifmm_rays: n_rays must be >= 1");
@@ -1300,6 +1300,10 @@ static int rays_launch(alifmm_ctx *c, int32_t n_rays, const int32_t *src_iz, con
         if (smem > 200 * 1024) return fail(ALIFMM_E_INVALID, "alifmm_rays: subgrid too large for the ray kernel's shared memory");
         CUDA_TRY(cudaFuncSetAttribute(ali_rays_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
+    if (zero_paths) {   // the whole [n_rays][cap] block goes to the caller: no stale bytes of a recycled buffer behind a path
+        CUDA_TRY(cudaMemsetAsync(a.out_x, 0, (size_t)n_rays * cap * sizeof(double), s));
+        CUDA_TRY(cudaMemsetAsync(a.out_y, 0, (size_t)n_rays * cap * sizeof(double), s));
+    }
     CUDA_TRY(cudaEventRecord(c->ev[3], s));
     ali_rays_kernel<<<(n_rays + ALI_RAY_WARPS - 1) / ALI_RAY_WARPS, 32 * ALI_RAY_WARPS, smem, s>>>(a);
     CUDA_TRY(cudaGetLastError());
@@ -1325,7 +1329,7 @@ extern "C" int alifmm_rays(alifmm_ctx *c, int32_t n_rays, const int32_t *src_iz,
     if (!c || !src_iz || !src_ix || !rec_slot || !out_len || !out_time)
         return fail(ALIFMM_E_INVALID, "alifmm_rays: null argument");
     AliRayArgs a;
-    int rc = rays_launch(c, n_rays, src_iz, src_ix, rec_slot, cap, a);
+    int rc = rays_launch(c, n_rays, src_iz, src_ix, rec_slot, cap, a, out_x != nullptr || out_y != nullptr);
     if (rc != ALIFMM_OK) return rc;
     cudaStream_t s = c->stream;
     CUDA_TRY(cudaMemcpyAsync(out_len, a.out_len, (size_t)n_rays * sizeof(int), cudaMemcpyDeviceToHost, s));

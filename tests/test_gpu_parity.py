@@ -457,6 +457,8 @@ def test_rays_into_dense_layout_equals_plain_rays(capi):
     slots = [0, 1, 0, 1, 1, 0]
     cap = 5 * (60 + 80)
     x, y, ln, tm, fl = ctx.rays(siz, six, slots, cap)
+    for r in range(len(srcs)):
+        assert not x[r, ln[r]:].any() and not y[r, ln[r]:].any()   # zeros behind a path, also from a recycled buffer
     bx, by = np.full((4, 5, cap), -7.0), np.full((4, 5, cap), -7.0)
     rows = np.array([3, 19, 0, 7, 12, 8])
     ln2, tm2, fl2 = ctx.rays_into(siz, six, slots, cap, sg, rows, bx, by)
