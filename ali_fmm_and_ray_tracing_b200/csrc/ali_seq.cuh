@@ -159,10 +159,18 @@ ALI_DEV void ali_downtree(AliSeqGrid &g)
     ntr -= 1;
     int tpp = 1, tpc = 2;
     bool moved = false;
+    // The keys of a level's pair are loaded one level ahead (for both candidates), so that the chain
+    // per level is compare + select instead of load + compare.  Only the hole position is written
+    // on the way down, never a position below it: what was loaded ahead stays valid.
+    double ka = (tpc <= ntr) ? g.hkey[tpc] : 0.0, kb = (tpc + 1 <= ntr) ? g.hkey[tpc + 1] : 0.0;
     while (tpc < ntr) {
-        double rd1 = g.hkey[tpc];
-        const double rd2 = g.hkey[tpc + 1];
-        if (rd1 > rd2) { tpc += 1; rd1 = rd2; }
+        const int ga = 2 * tpc, gb = ga + 2;
+        const double gaa = (ga <= ntr) ? g.hkey[ga] : 0.0, gab = (ga + 1 <= ntr) ? g.hkey[ga + 1] : 0.0;
+        const double gba = (gb <= ntr) ? g.hkey[gb] : 0.0, gbb = (gb + 1 <= ntr) ? g.hkey[gb + 1] : 0.0;
+        double rd1 = ka;
+        const double rd2 = kb;
+        bool second = false;
+        if (rd1 > rd2) { tpc += 1; rd1 = rd2; second = true; }
         if (rd1 < kv) {
             const AliHeapEnt ce = g.heap[tpc];
             g.st[le.wi] = tpc;
@@ -171,13 +179,15 @@ ALI_DEV void ali_downtree(AliSeqGrid &g)
             g.hkey[tpp] = rd1;
             tpp = tpc;
             tpc = 2 * tpp;
+            ka = second ? gba : gaa;
+            kb = second ? gbb : gab;
             moved = true;
         } else {
             tpc = ntr + 1;
         }
     }
     if (tpc == ntr) {
-        const double rd1 = g.hkey[tpc];
+        const double rd1 = ka;   // == g.hkey[tpc]
         if (rd1 < kv) {
             const AliHeapEnt ce = g.heap[tpc];
             g.st[le.wi] = tpc;
