@@ -107,6 +107,57 @@ def _split(items, parts):
     return out
 
 
+def _axis_velocity(a, c_22, c_33, density):
+    """Velocity along a symmetry axis (a = 0 or 90 degrees): sqrt(c / rho), exact special case of the
+    reference's curves (ATR:4134-4139, 4183-4188)."""
+    return math.sqrt((c_33 if a == 90 else c_22) / density)
+
+
+def _group_sample(a, c_22, c_23, c_33, c_44, density):
+    """Christoffel group velocity at a whole degree 0 <= a < 180 (closed form of ATR:4141-4152:
+    phase angle from the quadratic in tan, then the group speed along the ray direction)."""
+    if a % 90 == 0:
+        return _axis_velocity(a, c_22, c_33, density)
+    rad = math.radians(a)
+    t = math.tan(rad)
+    A = c_22 + c_33 - 2 * c_44
+    B = (c_23 + c_44) * (t - 1 / t)
+    C = c_22 - c_33
+    root = math.sqrt(B ** 2 + A ** 2 - C ** 2)
+    phi = math.atan((-B - root if a < 90 else -B + root) / (C - A)) % math.pi
+    lam = 0.5 * (math.cos(2 * phi) * (c_22 - c_44) + math.sin(2 * phi) * (c_23 + c_44) * t + c_22 + c_44)
+    return math.sqrt(lam / density) / math.cos(rad - phi)
+
+
+def _phase_sample(a, c_22, c_23, c_33, c_44, density):
+    """Christoffel phase velocity at a whole degree 0 <= a < 180 (ATR:4190-4197)."""
+    if a % 90 == 0:
+        return _axis_velocity(a, c_22, c_33, density)
+    co = math.cos(math.radians(a))
+    si = math.sin(math.radians(a))
+    A = co ** 2 * c_22 + si ** 2 * c_44
+    B = co * si * (c_23 + c_44)
+    C = co ** 2 * c_44 + si ** 2 * c_33
+    return math.sqrt((A + C + math.sqrt((A - C) ** 2 + 4 * B ** 2)) / (2 * density))
+
+
+def _mirror_curve(half):
+    """361 samples from the 180 of the upper half plane: the curves are pi-periodic (ATR:4154, 4200)."""
+    curve = np.empty(361)
+    curve[0:180] = half
+    curve[180:360] = half
+    curve[360] = half[0]
+    return curve
+
+
+def _polar_plot(curve, title):
+    plt = _plt()
+    if plt is not None:
+        plt.polar(math.pi / 180 * np.arange(0, 361), curve)
+        plt.title(title)
+        plt.show()
+
+
 class ALI_FMM:
     """Travel time fields and ray tracing in anisotropic media (reference: ATR:3789)."""
 
@@ -321,111 +372,65 @@ class ALI_FMM:
         plt.show()
 
     def generate_group_vel(self, c_22, c_23, c_33, c_44, density, plot=True):
-        """Group velocity curve (361 samples, 1 degree) of a material (ATR:4112).  Host-side
-        table set-up, arithmetic as in the reference; callable with ``None`` as self."""
-        group_vel = np.zeros(361)
-        for angle in range(361):
-            if angle < 180:
-                if angle % 90 == 0:
-                    if angle % 180 == 90:
-                        lambda_val = c_33
-                    else:
-                        lambda_val = c_22
-                    velocity = math.sqrt(lambda_val / density)
-                else:
-                    tan_ang = math.tan(math.radians(angle))
-                    A = c_22 + c_33 - 2 * c_44
-                    B = (c_23 + c_44) * (tan_ang - 1 / tan_ang)
-                    C = c_22 - c_33
-                    if angle < 90:
-                        phase_angle_rad = math.atan((-B - math.sqrt(B ** 2 + A ** 2 - C ** 2)) / (C - A)) % math.pi
-                    else:
-                        phase_angle_rad = math.atan((-B + math.sqrt(B ** 2 + A ** 2 - C ** 2)) / (C - A)) % math.pi
-                    lambda_val = 0.5 * (math.cos(2 * phase_angle_rad) * (c_22 - c_44) + math.sin(2 * phase_angle_rad) * (c_23 + c_44) * tan_ang + c_22 + c_44)
-                    velocity = math.sqrt(lambda_val / density) / math.cos(math.radians(angle) - phase_angle_rad)
-                group_vel[angle] = velocity
-            else:
-                group_vel[angle] = group_vel[angle - 180]
+        """Group velocity curve of a material: 361 samples at 1 degree, stiffness in Pa (ATR:4112).
+        Callable with ``None`` as self, as the reference's documentation does."""
+        curve = _mirror_curve([_group_sample(a, c_22, c_23, c_33, c_44, density) for a in range(180)])
         if plot == True:
-            plt = _plt()
-            if plt is not None:
-                plt.polar(math.pi / 180 * np.arange(0, 361), group_vel)
-                plt.title("Group Velocity")
-                plt.show()
-        return group_vel
+            _polar_plot(curve, "Group Velocity")
+        return curve
 
     def generate_phase_vel(self, c_22, c_23, c_33, c_44, density, plot=True):
-        """Phase velocity curve (361 samples, 1 degree) of a material (ATR:4162)."""
-        phase_vel = np.zeros(361)
-        for angle in range(361):
-            if angle < 180:
-                if angle % 90 == 0:
-                    if angle % 180 == 90:
-                        lambda_val = c_33
-                    else:
-                        lambda_val = c_22
-                    velocity = math.sqrt(lambda_val / density)
-                else:
-                    cos_ang = math.cos(math.radians(angle))
-                    sin_ang = math.sin(math.radians(angle))
-                    A = cos_ang ** 2 * c_22 + sin_ang ** 2 * c_44
-                    B = cos_ang * sin_ang * (c_23 + c_44)
-                    C = cos_ang ** 2 * c_44 + sin_ang ** 2 * c_33
-                    velocity = math.sqrt((A + C + math.sqrt((A - C) ** 2 + 4 * B ** 2)) / (2 * density))
-                phase_vel[angle] = velocity
-            else:
-                phase_vel[angle] = phase_vel[angle - 180]
+        """Phase velocity curve of a material: 361 samples at 1 degree, stiffness in Pa (ATR:4162)."""
+        curve = _mirror_curve([_phase_sample(a, c_22, c_23, c_33, c_44, density) for a in range(180)])
         if plot == True:
-            plt = _plt()
-            if plt is not None:
-                plt.polar(math.pi / 180 * np.arange(0, 361), phase_vel)
-                plt.title("Phase Velocity")
-                plt.show()
-        return phase_vel
+            _polar_plot(curve, "Phase Velocity")
+        return curve
 
     def add_materials(self, materials, keep_materials=False):
-        """Replaces / extends the velocity tables from stiffness tensors in Pa (ATR:4208),
-        including the reference's table sizing by ``materials.shape[1]``."""
-        gen_g = lambda m: ALI_FMM.generate_group_vel(self, m[0], m[1], m[2], m[3], m[4], False)
-        gen_p = lambda m: ALI_FMM.generate_phase_vel(self, m[0], m[1], m[2], m[3], m[4], False)
+        """Replaces (default) or extends (``keep_materials``) the velocity tables with the curves of
+        ``materials`` -- one (c22, c23, c33, c44 [Pa], density) row, or a 2-D array of rows (ATR:4208).
+        The table widths follow the reference, including its sizing of 2-D input by
+        ``materials.shape[1]`` (ATR:4228-4231, 4243-4252).  With ``options["tables_on_device"]`` the
+        curves of all rows come from one alifmm_velocity_curves_batch launch."""
+        materials = np.asarray(materials)
+        rows = materials[None, :] if materials.ndim == 1 else materials
+        old_g, old_p = self.velocity_dat, self.phase_vel
+        n_old = old_g.shape[1]
+        if keep_materials == True:
+            first = n_old
+            n_fill = 1 if materials.ndim == 1 else materials.shape[0]
+            width = n_old + (1 if materials.ndim == 1 else materials.shape[1])
+        else:
+            first = 1
+            n_fill = 1 if materials.ndim == 1 else materials.shape[1]   # (the reference loops over shape[1] here)
+            width = 1 + n_fill
+        if rows.shape[0] < n_fill or first + n_fill > width:
+            # the reference indexes past its arrays in these cases (ATR:4232-4235, 4249-4252)
+            raise IndexError("add_materials: %d material rows do not fit the reference's table sizing" % rows.shape[0])
+        curves_g, curves_p = self._material_curves(rows[:n_fill])
+        tables = []
+        for old, curves in ((old_g, curves_g), (old_p, curves_p)):
+            tab = np.zeros((361, width))
+            if keep_materials == True:
+                tab[:, :n_old] = old
+            else:
+                tab[:, 0] = np.arange(0, 361)
+            tab[:, first:first + n_fill] = curves.T
+            tables.append(tab)
         if keep_materials == True:
             if materials.ndim == 1:
-                group_vel_data = np.zeros((361, self.velocity_dat.shape[1] + 1))
-                group_vel_data[:, 0:self.velocity_dat.shape[1]] = self.velocity_dat
-                group_vel_data[:, group_vel_data.shape[1] - 1] = gen_g(materials)
-                phase_vel_data = np.zeros((361, self.phase_vel.shape[1] + 1))
-                phase_vel_data[:, 0:self.velocity_dat.shape[1]] = self.phase_vel
-                phase_vel_data[:, group_vel_data.shape[1] - 1] = gen_p(materials)
-                print("material id of new material is " + str(self.velocity_dat.shape[1]))
+                print("material id of new material is " + str(n_old))
             else:
-                group_vel_data = np.zeros((361, self.velocity_dat.shape[1] + materials.shape[1]))
-                group_vel_data[:, 0:self.velocity_dat.shape[1]] = self.velocity_dat
-                phase_vel_data = np.zeros((361, self.velocity_dat.shape[1] + materials.shape[1]))
-                phase_vel_data[:, 0:self.velocity_dat.shape[1]] = self.phase_vel
-                for i in range(materials.shape[0]):
-                    index = i + self.velocity_dat.shape[1]
-                    group_vel_data[:, index] = gen_g(materials[i])
-                    phase_vel_data[:, index] = gen_p(materials[i])
-                print("material id's of new materials are " + str(self.velocity_dat.shape[1]) + " - " + str(self.velocity_dat.shape[1] + materials.shape[0] - 1))
-        else:
-            if materials.ndim == 1:
-                group_vel_data = np.zeros((361, 2))
-                phase_vel_data = np.zeros((361, 2))
-            else:
-                group_vel_data = np.zeros((361, materials.shape[1] + 1))
-                phase_vel_data = np.zeros((361, materials.shape[1] + 1))
-            group_vel_data[:, 0] = np.arange(0, 361)
-            phase_vel_data[:, 0] = np.arange(0, 361)
-            if materials.ndim == 1:
-                group_vel_data[:, 1] = gen_g(materials)
-                phase_vel_data[:, 1] = gen_p(materials)
-            else:
-                for i in range(materials.shape[1]):
-                    index = i + 1
-                    group_vel_data[:, index] = gen_g(materials[i])
-                    phase_vel_data[:, index] = gen_p(materials[i])
-        self.velocity_dat = group_vel_data
-        self.phase_vel = phase_vel_data
+                print("material id's of new materials are " + str(n_old) + " - " + str(n_old + materials.shape[0] - 1))
+        self.velocity_dat, self.phase_vel = tables
+
+    def _material_curves(self, rows):
+        """Group / phase curves of the material rows, float64 [n, 361] each."""
+        if getattr(self, "options", None) and self.options.get("tables_on_device"):
+            return _capi.velocity_curves_batch(np.asarray(rows, dtype=np.float64), device=_device_list()[0])
+        g = np.array([ALI_FMM.generate_group_vel(self, r[0], r[1], r[2], r[3], r[4], False) for r in rows])
+        p = np.array([ALI_FMM.generate_phase_vel(self, r[0], r[1], r[2], r[3], r[4], False) for r in rows])
+        return g.reshape(len(rows), 361), p.reshape(len(rows), 361)
 
     # ------------------------------------------------------------------ rays
     def _default_pairs(self, n_trans):

@@ -46,6 +46,7 @@ EXPORTS = [
     "alifmm_ttf", "alifmm_ttf_fetch", "alifmm_ttf_shape", "alifmm_rays", "alifmm_rays_into", "alifmm_trim",
     "alifmm_mem_info", "alifmm_counters",
     "alifmm_velocity_curves", "alifmm_min_max_vel", "alifmm_last_error",
+    "alifmm_velocity_curves_batch", "alifmm_eval_nodes",
 ]
 
 _lib = None
@@ -85,6 +86,10 @@ def load():
     lib.alifmm_velocity_curves.argtypes = [vp] + [ctypes.c_double] * 5 + [_f64p, _f64p]
     lib.alifmm_min_max_vel.argtypes = [vp, _f64p, _f64p]
     lib.alifmm_last_error.restype = ctypes.c_char_p
+    lib.alifmm_velocity_curves_batch.argtypes = [ctypes.c_int, ctypes.c_int32, _f64p, _f64p, _f64p]
+    lib.alifmm_eval_nodes.argtypes = [ctypes.c_int, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_double, _f64p,
+                                      _i32p, _f64p, _i64p, ctypes.c_int32, _f64p, _f64p, ctypes.c_int32, _f64p, _i32p,
+                                      _i32p, _f64p, _f64p, _i32p]
     _lib = lib
     return lib
 
@@ -105,6 +110,44 @@ def device_count():
 
 def _ptr(a, t):
     return a.ctypes.data_as(t) if a is not None else None
+
+
+def velocity_curves_batch(materials, device=0):
+    """Group and phase velocity curves of a batch of materials on the device: ``materials`` [n, 5] =
+    (c22, c23, c33, c44 [Pa], density); returns (group, phase), float64 [n, 361] each."""
+    props = np.ascontiguousarray(np.atleast_2d(materials), dtype=np.float64)
+    if props.ndim != 2 or props.shape[1] != 5:
+        raise ValueError("materials must have shape (n, 5)")
+    n = props.shape[0]
+    g = np.zeros((n, 361))
+    p = np.zeros((n, 361))
+    _check(load().alifmm_velocity_curves_batch(int(device), n, _ptr(props, _f64p), _ptr(g, _f64p), _ptr(p, _f64p)))
+    return g, p
+
+
+def eval_nodes(veln, velpn, vel_map, stif_den, has_stif, group_vel, phase_vel, dnx, ttn, nsts, pos, device=0):
+    """Device update() / fouds18_A() on n independent states ([n, nz, nx] arrays, pos [n, 2] = (iz, ix)).
+    Returns (out_update, out_fouds, stencil_no)."""
+    veln = np.ascontiguousarray(veln, dtype=np.float64)
+    n, nz, nx = veln.shape
+    velpn = np.ascontiguousarray(velpn, dtype=np.int32)
+    vel_map = np.ascontiguousarray(vel_map, dtype=np.float64)
+    stif = None if stif_den is None else np.ascontiguousarray(stif_den, dtype=np.int64)
+    group = np.ascontiguousarray(group_vel, dtype=np.float64)
+    phase = np.ascontiguousarray(phase_vel, dtype=np.float64)
+    ttn = np.ascontiguousarray(ttn, dtype=np.float64)
+    nsts = np.ascontiguousarray(nsts, dtype=np.int32)
+    pos = np.ascontiguousarray(pos, dtype=np.int32)
+    assert velpn.shape == veln.shape == vel_map.shape == ttn.shape == nsts.shape and pos.shape == (n, 2)
+    assert group.shape == phase.shape and group.shape[0] == 361
+    ou = np.zeros(n)
+    of = np.zeros(n)
+    os_ = np.zeros(n, dtype=np.int32)
+    _check(load().alifmm_eval_nodes(int(device), n, nz, nx, float(dnx), _ptr(veln, _f64p), _ptr(velpn, _i32p),
+                                    _ptr(vel_map, _f64p), _ptr(stif, _i64p), int(bool(has_stif)), _ptr(group, _f64p),
+                                    _ptr(phase, _f64p), group.shape[1], _ptr(ttn, _f64p), _ptr(nsts, _i32p),
+                                    _ptr(pos, _i32p), _ptr(ou, _f64p), _ptr(of, _f64p), _ptr(os_, _i32p)))
+    return ou, of, os_
 
 
 class Context:

@@ -30,6 +30,7 @@
 #define ALI_T_UNSET_BYTE 0xFF
 #define ALI_T_FAR_BITS 0xFFFFFFFFFFFFFFFFull
 #define ALI_T_ENLISTED_BITS 0xFFFFFFFFFFFFFFFEull
+#define ALI_T_NAN_VALUE_BITS 0x7FF8000000000001ll   /* a computed NaN (degenerate material), canonicalised */
 
 // Band list entries pack the node as (iz << 16) | ix (grids up to 65535 x 65535).
 #define ALI_PACK(iz, ix) (((unsigned)(iz) << 16) | (unsigned)(ix))

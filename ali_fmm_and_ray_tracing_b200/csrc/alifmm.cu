@@ -89,11 +89,12 @@ struct AliBatch {
 // ---------------------------------------------------------------------------
 // Builds the 64-byte per-node material records from the caller's arrays.
 __global__ void ali_records_kernel(int n, const double *veln, const int32_t *velpn, const double *vel_map,
-                                   const long long *stif, AliMatRec *rec)
+                                   const long long *stif, AliMatRec *rec, int *bad)
 {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         AliMatRec r;
         r.veln = veln[i]; r.vel_map = vel_map[i]; r.velpn = velpn[i]; r.pad = 0;
+        if (bad && (!isfinite(r.veln) || !isfinite(r.vel_map))) atomicOr(bad, 1);
         for (int k = 0; k < 5; k++) r.s[k] = stif ? (double)stif[(size_t)5 * i + k] : 0.0;
         rec[i] = r;
     }
@@ -360,7 +361,8 @@ __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
             const int iz = ALI_PACK_Z(e), ix = ALI_PACK_X(e);
             int fb = 0;
             const double vold = val[i];   // the value this node last published (0: none yet)
-            const double v = ali_band_eval(b.m, b.m_dev, g, &s_grid, iz, ix, &fb, s_sincos);
+            double v = ali_band_eval(b.m, b.m_dev, g, &s_grid, iz, ix, &fb, s_sincos);
+            if (v != v) v = __longlong_as_double(ALI_T_NAN_VALUE_BITS);   // never the far / enlisted codes
             val[i] = v;
             my_evals++;
             my_fbs += fb;
@@ -414,7 +416,7 @@ __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
                 const unsigned e = ent[i];
                 v = val[i];
                 const int iz = ALI_PACK_Z(e), ix = ALI_PACK_X(e);
-                if (v <= thr) {
+                if (!(v > thr)) {   // also a NaN value (degenerate material): the reference pops it too; never loops
                     k = ali_band_accept(g, iz, ix, out); // new nodes: always evaluated next round
                     kw = k;
                     v = 0.0;
@@ -445,7 +447,7 @@ __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
             atomicMin(&s_basemin[cur ^ 1], (unsigned long long)__double_as_longlong(bmin));
         __syncthreads();
         if (tid == 0) { const long long now = clock64(); s_cyc[2] += now - s_tprev; s_tprev = now; }
-        if (resort && s_count[cur ^ 1] > 64 && !s_overflow) {
+        if (resort && !s_overflow) {   // (any list length: phase C left the work list / base minimum to this pass)
             // counting sort of the new list by angular bin, from the "next" buffers back into the
             // current ones (free now); then the work list / base minimum on the sorted order
             const int nn = s_count[cur ^ 1];
@@ -543,15 +545,17 @@ __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
 // Tiled march field -> the caller's row-major field, T / subgrid (ATR:2832); nodes the march never
 // reached get the reference's 0.  A warp reads 8 sectors of 8 tiles and writes 256 contiguous bytes;
 // the other three rows of those tiles are read by the next rows' warps out of L2.
-__global__ void ali_finalize_kernel(const double *Tt, double *T, int n_src, int nz, int nx, size_t tn, int sg)
+__global__ void ali_finalize_kernel(const double *Tt, const uint8_t *st, double *T, int n_src, int nz, int nx, size_t tn, int sg)
 {
     const size_t N = (size_t)nz * nx, total = (size_t)n_src * N;
     const size_t t4x = (size_t)((nx + 3) >> 2);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const size_t src = i / N, r = i - src * N;
         const int z = (int)(r / nx), x = (int)(r - (size_t)z * nx);
-        const double v = Tt[src * tn + ((((size_t)(z >> 2) * t4x + (size_t)(x >> 2)) << 4) | (size_t)(((z & 3) << 2) | (x & 3)))];
-        T[i] = (v >= 0.0) ? v / sg : 0.0;
+        const size_t node = src * tn + ((((size_t)(z >> 2) * t4x + (size_t)(x >> 2)) << 4) | (size_t)(((z & 3) << 2) | (x & 3)));
+        const double v = Tt[node];
+        // an accepted node without a number (NaN material / velocity) stays NaN, as in the reference
+        T[i] = (v >= 0.0) ? v / sg : ((v != v && __double_as_longlong(v) == ALI_T_NAN_VALUE_BITS && st[node] == ALI_ST_ALIVE) ? v : 0.0);
     }
 }
 
@@ -650,38 +654,89 @@ __global__ void __launch_bounds__(32 * ALI_RAY_WARPS) ali_rays_kernel(AliRayArgs
     }
 }
 
-// generate_group_vel / generate_phase_vel (ATR:4112-4206): one thread per degree.
+// generate_group_vel / generate_phase_vel (ATR:4112-4206) at one whole degree a in 0..360 (stiffness in
+// Pa, no factor 1000; exact special cases at multiples of 90; 180..360 mirror 0..180, ATR:4154, 4200).
+__device__ __forceinline__ void ali_curve_point(int a, double c22, double c23, double c33, double c44, double rho,
+                                                double &gv, double &pv)
+{
+    int angle = a < 180 ? a : a - 180;
+    if (angle >= 180) angle -= 180;   // 360 -> 180 -> index 0
+    if (angle % 90 == 0) {
+        const double lam = (angle % 180 == 90) ? c33 : c22;
+        gv = sqrt(lam / rho);
+        pv = gv;
+        return;
+    }
+    const double rad = ALI_DEG2RAD * angle;
+    const double t = ALI_TAN(rad);
+    const double A = c22 + c33 - 2 * c44;
+    const double B = (c23 + c44) * (t - 1 / t);
+    const double C = c22 - c33;
+    const double disc = sqrt(B * B + A * A - C * C);
+    double ph;
+    if (angle < 90) ph = ali_pymod(ALI_ATAN((-B - disc) / (C - A)), ALI_PI);
+    else ph = ali_pymod(ALI_ATAN((-B + disc) / (C - A)), ALI_PI);
+    const double lam = 0.5 * (ALI_COS(2 * ph) * (c22 - c44) + ALI_SIN(2 * ph) * (c23 + c44) * t + c22 + c44);
+    gv = sqrt(lam / rho) / ALI_COS(rad - ph);
+    const double cs = ALI_COS(rad), sn = ALI_SIN(rad);
+    const double A2 = cs * cs * c22 + sn * sn * c44;
+    const double B2 = cs * sn * (c23 + c44);
+    const double C2 = cs * cs * c44 + sn * sn * c33;
+    pv = sqrt((A2 + C2 + sqrt((A2 - C2) * (A2 - C2) + 4 * (B2 * B2))) / (2 * rho));
+}
+
 __global__ void ali_curves_kernel(double c22, double c23, double c33, double c44, double rho, double *group,
                                   double *phase)
 {
-    int a = blockIdx.x * blockDim.x + threadIdx.x;
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a > 360) return;
-    int angle = a < 180 ? a : a - 180; // 180..360 mirror 0..180 (ATR:4154, 4200); 360 -> 180 -> index 0
-    if (angle >= 180) angle -= 180;
-    double gv, pv;
-    if (angle % 90 == 0) {
-        double lam = (angle % 180 == 90) ? c33 : c22;
-        gv = sqrt(lam / rho);
-        pv = gv;
-    } else {
-        double t = tan(ALI_DEG2RAD * angle);
-        double A = c22 + c33 - 2 * c44;
-        double B = (c23 + c44) * (t - 1 / t);
-        double C = c22 - c33;
-        double disc = sqrt(B * B + A * A - C * C);
-        double ph;
-        if (angle < 90) ph = ali_pymod(atan((-B - disc) / (C - A)), ALI_PI);
-        else ph = ali_pymod(atan((-B + disc) / (C - A)), ALI_PI);
-        double lam = 0.5 * (cos(2 * ph) * (c22 - c44) + sin(2 * ph) * (c23 + c44) * t + c22 + c44);
-        gv = sqrt(lam / rho) / cos(ALI_DEG2RAD * angle - ph);
-        double cs = cos(ALI_DEG2RAD * angle), sn = sin(ALI_DEG2RAD * angle);
-        double A2 = cs * cs * c22 + sn * sn * c44;
-        double B2 = cs * sn * (c23 + c44);
-        double C2 = cs * cs * c44 + sn * sn * c33;
-        pv = sqrt((A2 + C2 + sqrt((A2 - C2) * (A2 - C2) + 4 * (B2 * B2))) / (2 * rho));
-    }
-    group[a] = gv;
-    phase[a] = pv;
+    ali_curve_point(a, c22, c23, c33, c44, rho, group[a], phase[a]);
+}
+
+// The same curves for a batch of materials (add_materials, ATR:4208-4256): props[n_mat][5] in Pa,
+// outputs [n_mat][361].  One thread per (material, degree).
+__global__ void ali_curves_batch_kernel(int n_mat, const double *props, double *group, double *phase)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_mat * 361) return;
+    const int mat = t / 361, a = t - mat * 361;
+    const double c22 = props[5 * mat], c23 = props[5 * mat + 1], c33 = props[5 * mat + 2], c44 = props[5 * mat + 3],
+                 rho = props[5 * mat + 4];
+    ali_curve_point(a, c22, c23, c33, c44, rho, group[t], phase[t]);
+}
+
+// Node-level operator check (test entry alifmm_eval_nodes): one thread per caller-supplied state
+// runs the ALI update (ATR:904-1410) and the FD fallback (ATR:240-901) exactly as the kernels do.
+struct AliNodeState {
+    int nz, nx;
+    const double *t;
+    const int32_t *st;
+    ALI_DEV bool in(int z, int x) const { return z >= 0 && z < nz && x >= 0 && x < nx; }
+    ALI_DEV bool avail(int z, int x) const { return in(z, x) && st[z * nx + x] >= 0; }
+    ALI_DEV bool alive(int z, int x) const { return in(z, x) && st[z * nx + x] == 0; }
+    ALI_DEV double tt(int z, int x) const { return t[z * nx + x]; }
+};
+
+__global__ void ali_eval_nodes_kernel(int n, AliModel m0, const double *ttn, const int32_t *nsts, const int32_t *pos,
+                                      double *out_update, double *out_fouds, int32_t *out_stencil)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const int nn = m0.nz * m0.nx;
+    AliModel m = m0;
+    m.rec = m0.rec + (size_t)c * nn;
+    AliNodeState st;
+    st.nz = m.nz; st.nx = m.nx; st.t = ttn + (size_t)c * nn; st.st = nsts + (size_t)c * nn;
+    const int iz = pos[2 * c], ix = pos[2 * c + 1];
+    const AliMatView idv = ali_view_identity();
+    AliMat mat;
+    AliWindow w;
+    ali_fetch_mat(m, idv, iz, ix, mat);
+    ali_gather(st, iz, ix, m.nz, m.nx, w);
+    int stencil = 0;
+    out_update[c] = ali_update_window(m, mat, w, iz, ix, m.nz, m.nx, m.dnx, &stencil);
+    if (out_stencil) out_stencil[c] = stencil;
+    out_fouds[c] = ali_fouds18(m, mat, st, iz, ix, m.dnx, m.dnx, m.nx, m.nz);
 }
 
 // min_max_vel (ATR:3736-3787): group velocity at 0/45/90/135 degrees per node (Christoffel
@@ -837,25 +892,40 @@ static std::vector<PoolEntry> g_pin_pool;
 static void *pin_take(size_t bytes, size_t *got)
 {
     {
+        // best fit, and never a buffer more than twice the request (a big staging buffer handed out for a
+        // 64 MB chunk would force another big cudaHostAlloc later)
         std::lock_guard<std::mutex> lk(g_pool_mutex);
+        int best = -1;
         for (size_t i = 0; i < g_pin_pool.size(); i++)
-            if (g_pin_pool[i].bytes >= bytes) {
-                void *p = g_pin_pool[i].p;
-                *got = g_pin_pool[i].bytes;
-                g_pin_pool[i] = g_pin_pool.back();
-                g_pin_pool.pop_back();
-                return p;
-            }
+            if (g_pin_pool[i].bytes >= bytes && g_pin_pool[i].bytes <= 2 * bytes + (1 << 20) &&
+                (best < 0 || g_pin_pool[i].bytes < g_pin_pool[best].bytes))
+                best = (int)i;
+        if (best >= 0) {
+            void *p = g_pin_pool[best].p;
+            *got = g_pin_pool[best].bytes;
+            g_pin_pool[best] = g_pin_pool.back();
+            g_pin_pool.pop_back();
+            return p;
+        }
     }
     void *p = nullptr;
     if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     *got = bytes;
     return p;
 }
+#define ALI_PIN_POOL_MAX_BYTES ((size_t)1 << 30)   // page-locked memory kept for reuse, at most
 static void pin_give(void *p, size_t bytes)
 {
-    std::lock_guard<std::mutex> lk(g_pool_mutex);
-    g_pin_pool.push_back(PoolEntry{p, bytes, -1});
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mutex);
+        size_t held = 0;
+        for (const PoolEntry &e : g_pin_pool) held += e.bytes;
+        if (held + bytes <= ALI_PIN_POOL_MAX_BYTES) {
+            g_pin_pool.push_back(PoolEntry{p, bytes, -1});
+            return;
+        }
+    }
+    cudaFreeHost(p);
 }
 
 // Field results -> caller's (pageable) memory.  A plain cudaMemcpy into pageable memory runs at
@@ -994,10 +1064,19 @@ extern "C" int alifmm_create(const alifmm_model_desc *d, int device, alifmm_ctx 
         void *recp = recb.p;
         int blocks = (int)((n + 255) / 256);
         if (blocks > 148 * 8) blocks = 148 * 8;
-        ali_records_kernel<<<blocks, 256, 0, c->stream>>>((int)n, dv, dp, dm, ds, (AliMatRec *)recp);
-        if (cudaStreamSynchronize(c->stream) != cudaSuccess) {
+        if ((rc = dev_reserve(c->misc, 64)) != 0) { dev_release(recb, c->device); return bail(rc); }
+        int bad = 0;
+        if (cudaMemsetAsync(c->misc.p, 0, 64, c->stream) != cudaSuccess) { dev_release(recb, c->device); return bail(fail(ALIFMM_E_CUDA, "memset failed")); }
+        ali_records_kernel<<<blocks, 256, 0, c->stream>>>((int)n, dv, dp, dm, ds, (AliMatRec *)recp, (int *)c->misc.p);
+        if (cudaMemcpyAsync(&bad, c->misc.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+            cudaStreamSynchronize(c->stream) != cudaSuccess) {
             dev_release(recb, c->device);
             return bail(fail(ALIFMM_E_CUDA, std::string("alifmm_create: records kernel failed: ") + cudaGetErrorString(cudaGetLastError())));
+        }
+        if (bad) {
+            // a NaN / infinite orientation or velocity scale gives the reference a NaN field; here it is an error
+            dev_release(recb, c->device);
+            return bail(fail(ALIFMM_E_INVALID, "alifmm_create: veln / vel_map hold non-finite values"));
         }
         for (DevBuf &q : c->model_allocs) dev_release(q, c->device);
         c->model_allocs.clear();
@@ -1184,7 +1263,7 @@ static int ttf_attempt(alifmm_ctx *c, int32_t n_src, const int32_t *src_iz, cons
         size_t total = (size_t)n_src * N;
         int blocks = (int)((total + 255) / 256);
         if (blocks > 148 * 16) blocks = 148 * 16;
-        ali_finalize_kernel<<<blocks, 256, 0, s>>>(b.Tt, b.T, n_src, fz, fx, b.tn, sg);
+        ali_finalize_kernel<<<blocks, 256, 0, s>>>(b.Tt, b.st, b.T, n_src, fz, fx, b.tn, sg);
         CUDA_TRY(cudaGetLastError());
     }
     CUDA_TRY(cudaEventRecord(c->ev[3], s));
@@ -1499,5 +1578,99 @@ extern "C" int alifmm_min_max_vel(alifmm_ctx *c, double *min_vel, double *max_ve
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     memcpy(min_vel, &res[0], 8);
     memcpy(max_vel, &res[1], 8);
+    return ALIFMM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// context-free entries: material tables for a batch of materials, node-level operator check
+// ---------------------------------------------------------------------------
+static int pick_device(int device, const char *who)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(ALIFMM_E_CUDA, std::string(who) + ": no CUDA device available (this library has no CPU path)");
+    }
+    if (device < 0 || device >= ndev) return fail(ALIFMM_E_INVALID, std::string(who) + ": device index out of range");
+    CUDA_TRY(cudaSetDevice(device));
+    return ALIFMM_OK;
+}
+
+extern "C" int alifmm_velocity_curves_batch(int device, int32_t n_mat, const double *props, double *group_out,
+                                            double *phase_out)
+{
+    if (!props || !group_out || !phase_out) return fail(ALIFMM_E_INVALID, "alifmm_velocity_curves_batch: null argument");
+    if (n_mat < 1 || n_mat > 1000000) return fail(ALIFMM_E_INVALID, "alifmm_velocity_curves_batch: n_mat out of range");
+    int rc = pick_device(device, "alifmm_velocity_curves_batch");
+    if (rc != ALIFMM_OK) return rc;
+    const size_t np = (size_t)n_mat * 5, no = (size_t)n_mat * 361;
+    DevBuf buf;
+    if ((rc = dev_reserve(buf, (np + 2 * no) * sizeof(double))) != 0) return rc;
+    double *dp = (double *)buf.p, *dg = dp + np, *dph = dg + no;
+    cudaError_t e = cudaMemcpy(dp, props, np * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        ali_curves_batch_kernel<<<(int)((no + 127) / 128), 128>>>(n_mat, dp, dg, dph);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(group_out, dg, no * sizeof(double), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(phase_out, dph, no * sizeof(double), cudaMemcpyDeviceToHost);
+    dev_release(buf, device);
+    if (e != cudaSuccess) return fail(ALIFMM_E_CUDA, std::string("alifmm_velocity_curves_batch: ") + cudaGetErrorString(e));
+    return ALIFMM_OK;
+}
+
+extern "C" int alifmm_eval_nodes(int device, int32_t n, int32_t nz, int32_t nx, double dnx, const double *veln,
+                                 const int32_t *velpn, const double *vel_map, const int64_t *stif_den, int32_t has_stif,
+                                 const double *group_vel, const double *phase_vel, int32_t n_cols, const double *ttn,
+                                 const int32_t *nsts, const int32_t *pos, double *out_update, double *out_fouds,
+                                 int32_t *out_stencil)
+{
+    if (!veln || !velpn || !vel_map || !group_vel || !phase_vel || !ttn || !nsts || !pos || !out_update || !out_fouds)
+        return fail(ALIFMM_E_INVALID, "alifmm_eval_nodes: null argument");
+    if (n < 1 || nz < 1 || nx < 1 || n_cols < 1 || !(dnx > 0)) return fail(ALIFMM_E_INVALID, "alifmm_eval_nodes: bad sizes");
+    const size_t nn = (size_t)nz * nx, tot = (size_t)n * nn;
+    if (tot > 100000000u) return fail(ALIFMM_E_INVALID, "alifmm_eval_nodes: too many nodes");
+    for (size_t i = 0; i < tot; i++)
+        if (velpn[i] < 0 || velpn[i] >= n_cols) return fail(ALIFMM_E_INVALID, "alifmm_eval_nodes: velpn outside the velocity tables");
+    for (int c = 0; c < n; c++)
+        if (pos[2 * c] < 0 || pos[2 * c] >= nz || pos[2 * c + 1] < 0 || pos[2 * c + 1] >= nx)
+            return fail(ALIFMM_E_INVALID, "alifmm_eval_nodes: node outside its grid");
+    int rc = pick_device(device, "alifmm_eval_nodes");
+    if (rc != ALIFMM_OK) return rc;
+    std::vector<DevBuf> bufs;
+    auto cleanup = [&]() { for (DevBuf &b : bufs) dev_release(b, device); };
+    auto up = [&](const void *host, size_t bytes, void **out) -> int {
+        DevBuf b;
+        int r = dev_reserve(b, bytes < 8 ? 8 : bytes);
+        if (r != ALIFMM_OK) return r;
+        bufs.push_back(b);
+        if (host && cudaMemcpy(b.p, host, bytes, cudaMemcpyHostToDevice) != cudaSuccess)
+            return fail(ALIFMM_E_CUDA, "alifmm_eval_nodes: upload failed");
+        *out = b.p;
+        return ALIFMM_OK;
+    };
+    void *dv = nullptr, *dpn = nullptr, *dm = nullptr, *ds = nullptr, *dg = nullptr, *dph = nullptr, *dt = nullptr, *dst = nullptr,
+         *dpos = nullptr, *drec = nullptr, *dou = nullptr, *dof = nullptr, *dos = nullptr;
+    if ((rc = up(veln, tot * 8, &dv)) || (rc = up(velpn, tot * 4, &dpn)) || (rc = up(vel_map, tot * 8, &dm)) ||
+        (stif_den && (rc = up(stif_den, tot * 40, &ds))) || (rc = up(group_vel, (size_t)361 * n_cols * 8, &dg)) ||
+        (rc = up(phase_vel, (size_t)361 * n_cols * 8, &dph)) || (rc = up(ttn, tot * 8, &dt)) || (rc = up(nsts, tot * 4, &dst)) ||
+        (rc = up(pos, (size_t)n * 8, &dpos)) || (rc = up(nullptr, tot * sizeof(AliMatRec), &drec)) ||
+        (rc = up(nullptr, (size_t)n * 8, &dou)) || (rc = up(nullptr, (size_t)n * 8, &dof)) || (rc = up(nullptr, (size_t)n * 4, &dos))) {
+        cleanup();
+        return rc;
+    }
+    ali_records_kernel<<<(int)((tot + 255) / 256), 256>>>((int)tot, (const double *)dv, (const int32_t *)dpn, (const double *)dm,
+                                                         (const long long *)ds, (AliMatRec *)drec, nullptr);
+    AliModel m{};
+    m.nz = nz; m.nx = nx; m.rec = (const AliMatRec *)drec; m.has_stif = has_stif ? 1 : 0;
+    m.group_tab = (const double *)dg; m.phase_tab = (const double *)dph; m.ncol = n_cols; m.dnx = dnx;
+    ali_eval_nodes_kernel<<<(n + 63) / 64, 64>>>(n, m, (const double *)dt, (const int32_t *)dst, (const int32_t *)dpos,
+                                                (double *)dou, (double *)dof, (int32_t *)dos);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpy(out_update, dou, (size_t)n * 8, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(out_fouds, dof, (size_t)n * 8, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && out_stencil) e = cudaMemcpy(out_stencil, dos, (size_t)n * 4, cudaMemcpyDeviceToHost);
+    cleanup();
+    if (e != cudaSuccess) return fail(ALIFMM_E_CUDA, std::string("alifmm_eval_nodes: ") + cudaGetErrorString(e));
     return ALIFMM_OK;
 }

@@ -149,6 +149,26 @@ int alifmm_velocity_curves(alifmm_ctx *ctx, double c22, double c23, double c33, 
 /* Model sanity scan; replaces min_max_vel (ATR:3736-3787). */
 int alifmm_min_max_vel(alifmm_ctx *ctx, double *min_vel, double *max_vel);
 
+/* Christoffel curves of n_mat materials in one launch and one copy each way; replaces the per-material
+ * loop of ALI_FMM.add_materials (ATR:4208-4256 calling ATR:4112-4206).  props[n_mat][5] =
+ * (c22, c23, c33, c44 [Pa], density); outputs [n_mat][361] (row m = the 361 samples of material m).
+ * Needs no context (the class builds its tables before any model is uploaded). */
+int alifmm_velocity_curves_batch(int device, int32_t n_mat, const double *props, double *group_out, double *phase_out);
+
+/* Node-level operator check (used by the parity tests): runs the device restatements of update()
+ * (ATR:904-1410, with wavefront_angle_dist ATR:1413-1460) and of fouds18_A() (ATR:240-901) on n
+ * independent caller-supplied states.  State c is a grid of nz x nx nodes: model arrays
+ * veln/velpn/vel_map [n][nz*nx] (+ stif_den [n][nz*nx][5] or NULL), travel times ttn [n][nz*nx],
+ * statuses nsts [n][nz*nx] (-1 far, 0 alive, >0 narrow band, ATR:103) and the node pos[c] = (iz, ix).
+ * Outputs per state: out_update (-1.0 = no stencil, ATR:1408-1410), out_fouds (the value
+ * fouds18_A returns, including its min with ttn[iz, ix], ATR:898-899), out_stencil (may be NULL;
+ * 0-15 = stencil used, -1/-2 none as in ATR:989-1366). */
+int alifmm_eval_nodes(int device, int32_t n, int32_t nz, int32_t nx, double dnx, const double *veln,
+                      const int32_t *velpn, const double *vel_map, const int64_t *stif_den, int32_t has_stif,
+                      const double *group_vel, const double *phase_vel, int32_t n_cols, const double *ttn,
+                      const int32_t *nsts, const int32_t *pos, double *out_update, double *out_fouds,
+                      int32_t *out_stencil);
+
 const char *alifmm_last_error(void);
 
 #ifdef __cplusplus
