@@ -19,6 +19,7 @@ import threading
 import numpy as np
 
 from . import _capi
+from .sharding import split_list as _split
 
 try:  # progress bars are optional, as is the reference's module-level switch (ATR:22-24)
     from tqdm.auto import tqdm as _tqdm
@@ -94,17 +95,6 @@ def _zeros_sparse(shape):
     except (OSError, ValueError):
         pass
     return np.frombuffer(mm, dtype=np.float64).reshape(shape)
-
-
-def _split(items, parts):
-    """Contiguous, balanced partition of ``items`` into ``parts`` lists."""
-    k, r = divmod(len(items), parts)
-    out, pos = [], 0
-    for p in range(parts):
-        n = k + (1 if p < r else 0)
-        out.append(items[pos:pos + n])
-        pos += n
-    return out
 
 
 def _axis_velocity(a, c_22, c_33, density):
@@ -212,6 +202,7 @@ class ALI_FMM:
         self.ray_flags = None        # per-ray status bits instead of the reference's print (ATR:3407)
         self.last_counters = None    # work counters / device timings of the last call, per device
         self.options = {}            # alifmm_set_option() overrides, e.g. {"delta_frac": 0.25}
+        self.model_velocity_range = None   # (min, max) group velocity found by find_all_TTF_rays_parallel's model scan
 
     # ------------------------------------------------------------------ internals
     def _source_nodes(self, indices):
@@ -225,7 +216,8 @@ class ALI_FMM:
         ctx = _capi.Context(veln, velpn, vel_map, stif_den, True, self.velocity_dat, self.phase_vel, self.dnx,
                             device=device)
         for k, v in self.options.items():
-            ctx.set_option(k, v)
+            if k != "tables_on_device":   # (a host-side switch of add_materials, not a library option)
+                ctx.set_option(k, v)
         return ctx
 
     def _fields_per_batch(self, ctx, subgrid):
@@ -234,9 +226,11 @@ class ALI_FMM:
         per = fz * fx * self._BYTES_PER_NODE + (64 << 20)
         return max(1, int(free * self._MEM_FRACTION // per))
 
-    def _ttf_on_devices(self, veln, velpn, vel_map, stif_den, subgrid_size, indices, devices, sink):
-        """Computes the fields of transducers ``indices`` sharded over ``devices``;
-        ``sink(i, field)`` receives each field on the host."""
+    def _ttf_on_devices(self, veln, velpn, vel_map, stif_den, subgrid_size, indices, devices, dest, done=None):
+        """Computes the fields of transducers ``indices`` sharded over ``devices``.  Field i is
+        copied from the device straight into ``dest(i)`` (a C-contiguous float64 array of the
+        field's shape; fields stay in HBM until then -- no second host copy), then ``done(i, array)``
+        is called."""
         indices = list(indices)
         devices = devices[:max(1, min(len(devices), len(indices)))]
         shards = _split(indices, len(devices))
@@ -252,11 +246,15 @@ class ALI_FMM:
                     for pos in range(0, len(shard), step):
                         part = shard[pos:pos + step]
                         iz, ix = self._source_nodes(part)
-                        fields = ctx.ttf(iz, ix, subgrid_size)
-                        with lock:
-                            for k, i in enumerate(part):
-                                sink(i, fields[k])
-                        counters[d] = ctx.counters()
+                        ctx.ttf(iz, ix, subgrid_size, fetch=False)
+                        counters[d] = _merge_counters(counters[d], ctx.counters(), None)
+                        for slot, i in enumerate(part):
+                            with lock:
+                                out = dest(i)
+                            ctx.ttf_fetch(slot, out=out)
+                            if done is not None:
+                                with lock:
+                                    done(i, out)
                 finally:
                     ctx.close()
             except BaseException as e:  # re-raised in the caller's thread
@@ -318,8 +316,13 @@ class ALI_FMM:
             shape = (subgrid_size * (self.veln.shape[0] - 1) + 1, subgrid_size * (self.veln.shape[1] - 1) + 1)
         if low_mem:
             travel_time_field = None
+            spill = {}
 
-            def sink(i, field):
+            def dest(i):
+                # one buffer per worker thread, reused for every field it spills (ATR:3612-3615, 3660-3670)
+                return spill.setdefault(threading.get_ident(), np.empty(shape))
+
+            def done(i, field):
                 np.save("temp_TTF_" + str(i) + ".npy", field)
         else:
             if subgrid_size != 1 and not selected:
@@ -327,20 +330,21 @@ class ALI_FMM:
                 raise UnboundLocalError("travel_time_field: no source selected")
             travel_time_field = np.zeros((self.nsrc, shape[0], shape[1]))
 
-            def sink(i, field):
-                travel_time_field[i, :, :] = field
+            def dest(i):
+                return travel_time_field[i]
+
+            def done(i, field):
+                pass
         if selected:
             bar = _Bar(len(selected), "Finished TTF's")
-            counted = [0]
 
-            def counting_sink(i, field):
-                sink(i, field)
-                counted[0] += 1
+            def counting_done(i, field):
+                done(i, field)
                 bar.update(1)
 
             try:
                 self._ttf_on_devices(self.veln, self.velpn, self.vel_map, stif_den, subgrid_size, selected, devices,
-                                     counting_sink)
+                                     dest, counting_done)
             finally:
                 bar.close()
         return travel_time_field
@@ -349,10 +353,17 @@ class ALI_FMM:
         """Travel time field of one source (ATR:4053)."""
         if type(vel_map) == type(None):
             vel_map = np.ones(veln.shape)
-        out = []
-        self._ttf_on_devices(veln, velpn, vel_map, stif_den, subgrid_size, [source_i], _device_list()[:1],
-                             lambda i, f: out.append(np.array(f)))
-        return out[0]
+        ctx = self._context(veln, velpn, vel_map, stif_den, _device_list()[0])
+        try:
+            fz, fx = ctx.field_shape(subgrid_size)
+            out = np.empty((fz, fx))
+            iz, ix = self._source_nodes([source_i])
+            ctx.ttf(iz, ix, subgrid_size, fetch=False)
+            ctx.ttf_fetch(0, out=out)
+            self.last_counters = [ctx.counters()]
+        finally:
+            ctx.close()
+        return out
 
     # ------------------------------------------------------------------ material tables
     def plot_phase(self, material_index=1):
@@ -441,7 +452,8 @@ class ALI_FMM:
                     trans_pairs[i, j] = 1
         return trans_pairs
 
-    def _ttf_rays_impl(self, veln, velpn, vel_map, subgrid_size, trans_pairs, stif_den, save_rays, devices):
+    def _ttf_rays_impl(self, veln, velpn, vel_map, subgrid_size, trans_pairs, stif_den, save_rays, devices,
+                       scan_model=False):
         n_trans = len(self.isx)
         cap = 5 * (veln.shape[0] + veln.shape[1])
         if save_rays:
@@ -470,6 +482,11 @@ class ALI_FMM:
             try:
                 ctx = self._context(veln, velpn, vel_map, stif_den, devices[d])
                 try:
+                    if scan_model and d == 0:
+                        # the reference's model sanity scan (ATR:4583-4587; device reduction
+                        # alifmm_min_max_vel).  Like the reference -- whose Warning objects are built
+                        # but never raised -- nothing is printed; the range is kept for the caller.
+                        self.model_velocity_range = ctx.min_max_vel()
                     step = self._fields_per_batch(ctx, subgrid_size)
                     agg = None
                     for pos in range(0, len(shard), step):
@@ -543,8 +560,8 @@ class ALI_FMM:
             raise ValueError("n_threads should not equal one. Use find_all_TTF_rays for single process.")
         if type(vel_map) == type(None):
             vel_map = np.ones(veln.shape)
-        # model sanity scan of the reference (ATR:4583-4587): Warning objects are built, never raised
-        return self._ttf_rays_impl(veln, velpn, vel_map, subgrid_size, trans_pairs, stif_den, save_rays, _device_list())
+        return self._ttf_rays_impl(veln, velpn, vel_map, subgrid_size, trans_pairs, stif_den, save_rays, _device_list(),
+                                   scan_model=True)
 
     def ray_path(self, i, j):
         """Ray path from transducer i to j computed by find_all_TTF_rays* (ATR:4687)."""

@@ -35,7 +35,9 @@ class Counters(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int64) for n in (
         "node_solves", "seq_pops", "seq_evals", "band_rounds", "band_rounds_max", "band_evals", "fallback_evals",
         "max_band", "rays", "ray_points", "kernel_launches")] + [(n, ctypes.c_double) for n in (
-            "ms_seq", "ms_march", "ms_finalize", "ms_rays", "vmax", "delta")]
+            "ms_seq", "ms_march", "ms_finalize", "ms_rays", "vmax", "delta")] + [
+        ("cluster_size", ctypes.c_int64), ("seq_threads", ctypes.c_int64)] + [(n, ctypes.c_double) for n in (
+            "seq_mcycles_min", "seq_mcycles_max", "march_mcycles_min", "march_mcycles_max")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -219,6 +221,8 @@ class Context:
         n, fz, fx, _ = self.ttf_shape()
         if out is None:
             out = np.empty((fz, fx))
+        if out.dtype != np.float64 or not out.flags.c_contiguous or out.size != fz * fx:
+            raise ValueError("ttf_fetch: destination must be C-contiguous float64 of the field's size")
         _check(self._lib.alifmm_ttf_fetch(self._h, int(slot), _ptr(out, _f64p)))
         return out
 

@@ -14,8 +14,10 @@
 
 #if defined(__CUDACC__)
 #define ALI_SYNCWARP() __syncwarp()
+#define ALI_SYNCCTA() __syncthreads()   /* the sequential kernel runs one source per CTA (one or more warps) */
 #else
 #define ALI_SYNCWARP() ((void)0)
+#define ALI_SYNCCTA() ((void)0)
 #endif
 
 // Node state of one grid during the sequential march.  Status follows the reference:
@@ -70,20 +72,33 @@ ALI_DEV int ali_half_round(int k)
     return h;
 }
 
+// Keys beyond the heap's last entry hold +infinity (ali_seq_clear fills the whole array; a slot that
+// leaves the heap is reset), so the sift-down can load a level's four grandchild keys without
+// comparing indices with ntr: an absent child never wins.  The key array has ALI_HKEY_SLOTS(heap_cap)
+// entries so that the look-ahead of the last level stays inside it.
+#define ALI_HKEY_SLOTS(cap) (2 * (size_t)(cap) + 8)
+#if defined(__CUDA_ARCH__)
+#define ALI_KEY_NONE (__longlong_as_double(0x7ff0000000000000LL))
+#else
+#define ALI_KEY_NONE (HUGE_VAL)
+#endif
+
 // Sift-up shared by addtree / updtree (ATR:122-137, 159-174): the reference swaps the entry at
 // tpc with its parent while T(iz, ix) is smaller than the parent's time.  Here the parents move
 // down into the hole and the entry is stored once at the end (same final arrangement as the chain
-// of swaps); the status writes keep the reference's order, which matters for the nodes that sit
-// in the heap twice.  e0 / k0: the entry at tpc and its key.
+// of swaps).  The reference rewrites the status of the moving node at every swap; only the last
+// value survives unless a node sits in the heap twice (ndup > 0: the seed corners, level 0 only),
+// where the order of the status writes matters and is kept.  e0 / k0: the entry at tpc and its key.
 ALI_DEV void ali_sift_up_core(AliSeqGrid &g, unsigned wi_me, double tv, AliHeapEnt e0, double k0, int tpc)
 {
     int tpp = ali_half_round(tpc);
     bool moved = false;
+    const bool dups = g.ndup > 0;
     while (tpp > 0) {
         const double pk = g.hkey[tpp];
         if (tv < pk) {
             const AliHeapEnt pe = g.heap[tpp];
-            g.st[wi_me] = tpp;
+            if (dups) g.st[wi_me] = tpp;
             g.st[pe.wi] = tpc;
             g.heap[tpc] = pe;
             g.hkey[tpc] = pk;
@@ -94,7 +109,10 @@ ALI_DEV void ali_sift_up_core(AliSeqGrid &g, unsigned wi_me, double tv, AliHeapE
             tpp = 0;
         }
     }
-    if (moved) { g.heap[tpc] = e0; g.hkey[tpc] = k0; }
+    if (moved) {
+        g.heap[tpc] = e0; g.hkey[tpc] = k0;
+        if (!dups) g.st[wi_me] = tpc;
+    }
 }
 
 // updtree (ATR:141-175): called right after T(iz, ix) was rewritten, so the keys of the node's heap
@@ -104,7 +122,7 @@ ALI_DEV void ali_updtree_w(AliSeqGrid &g, int iz, int ix, unsigned wi_me)
 {
     const unsigned me = ((unsigned)iz << 16) | (unsigned)ix;
     const int tpc = g.st[wi_me];
-    const double tv = g.tt(iz, ix);
+    const double tv = g.t[wi_me];   // (T is window-indexed: t[z * t_stride + x - toff] == t[wi])
     const AliHeapEnt e0 = g.heap[tpc];
     double k0;
     if (e0.zx == me) { k0 = tv; g.hkey[tpc] = tv; }
@@ -126,7 +144,7 @@ ALI_DEV void ali_addtree_w(AliSeqGrid &g, int iz, int ix, unsigned wi_me)
 {
     if (g.ntr + 2 >= g.heap_cap) { g.overflow = 1; return; }
     const unsigned me = ((unsigned)iz << 16) | (unsigned)ix;
-    const double tv = g.tt(iz, ix);
+    const double tv = g.t[wi_me];
     if (g.st[wi_me] > 0) {   // second heap entry for a node (the reference pushes the seed corners twice)
         if (g.ndup == 0) g.dup0 = me; else if (g.ndup == 1) g.dup1 = me; else if (g.ndup == 2) g.dup2 = me;
         else if (g.ndup == 3) g.dup3 = me; else { g.overflow = 1; return; }
@@ -146,34 +164,35 @@ ALI_DEV void ali_addtree_w(AliSeqGrid &g, int iz, int ix, unsigned wi_me)
 ALI_DEV void ali_addtree(AliSeqGrid &g, int iz, int ix) { ali_addtree_w(g, iz, ix, (unsigned)g.widx(iz, ix)); }
 
 // downtree (ATR:178-237): the last entry replaces the root and sinks; children move up into the
-// hole, the entry is stored once at the end.
+// hole, the entry is stored once at the end.  The reference's two cases -- both children present
+// (ATR:196-221), only one (ATR:222-236) -- are one loop here: the absent sibling's key is +infinity.
 ALI_DEV void ali_downtree(AliSeqGrid &g)
 {
     int ntr = g.ntr;
-    if (ntr == 1) { g.ntr = 0; return; }
+    if (ntr == 1) { g.hkey[1] = ALI_KEY_NONE; g.ntr = 0; return; }
     const AliHeapEnt le = g.heap[ntr];
     const double kv = g.hkey[ntr];
+    g.hkey[ntr] = ALI_KEY_NONE;
     g.st[le.wi] = 1;
     g.heap[1] = le;
     g.hkey[1] = kv;
     ntr -= 1;
     int tpp = 1, tpc = 2;
     bool moved = false;
+    const bool dups = g.ndup > 0;
     // The keys of a level's pair are loaded one level ahead (for both candidates), so that the chain
     // per level is compare + select instead of load + compare.  Only the hole position is written
     // on the way down, never a position below it: what was loaded ahead stays valid.
-    double ka = (tpc <= ntr) ? g.hkey[tpc] : 0.0, kb = (tpc + 1 <= ntr) ? g.hkey[tpc + 1] : 0.0;
-    while (tpc < ntr) {
-        const int ga = 2 * tpc, gb = ga + 2;
-        const double gaa = (ga <= ntr) ? g.hkey[ga] : 0.0, gab = (ga + 1 <= ntr) ? g.hkey[ga + 1] : 0.0;
-        const double gba = (gb <= ntr) ? g.hkey[gb] : 0.0, gbb = (gb + 1 <= ntr) ? g.hkey[gb + 1] : 0.0;
-        double rd1 = ka;
-        const double rd2 = kb;
-        bool second = false;
-        if (rd1 > rd2) { tpc += 1; rd1 = rd2; second = true; }
+    double ka = g.hkey[2], kb = g.hkey[3];
+    while (tpc <= ntr) {
+        const int ga = 2 * tpc;
+        const double gaa = g.hkey[ga], gab = g.hkey[ga + 1], gba = g.hkey[ga + 2], gbb = g.hkey[ga + 3];
+        const bool second = ka > kb;
+        const double rd1 = second ? kb : ka;
+        tpc += second ? 1 : 0;
         if (rd1 < kv) {
             const AliHeapEnt ce = g.heap[tpc];
-            g.st[le.wi] = tpc;
+            if (dups) g.st[le.wi] = tpc;
             g.st[ce.wi] = tpp;
             g.heap[tpp] = ce;
             g.hkey[tpp] = rd1;
@@ -183,22 +202,13 @@ ALI_DEV void ali_downtree(AliSeqGrid &g)
             kb = second ? gbb : gab;
             moved = true;
         } else {
-            tpc = ntr + 1;
+            break;
         }
     }
-    if (tpc == ntr) {
-        const double rd1 = ka;   // == g.hkey[tpc]
-        if (rd1 < kv) {
-            const AliHeapEnt ce = g.heap[tpc];
-            g.st[le.wi] = tpc;
-            g.st[ce.wi] = tpp;
-            g.heap[tpp] = ce;
-            g.hkey[tpp] = rd1;
-            tpp = tpc;
-            moved = true;
-        }
+    if (moved) {
+        g.heap[tpp] = le; g.hkey[tpp] = kv;
+        if (!dups) g.st[le.wi] = tpp;
     }
-    if (moved) { g.heap[tpp] = le; g.hkey[tpp] = kv; }
     g.ntr = ntr;
 }
 
@@ -432,18 +442,23 @@ ALI_DEV int ali_coop_advance(AliSeqGrid &g, AliCoopState &cs, int cx, int cz, in
             if (inside) {
                 if (!g.in_win(z, x)) { cs.finished = 1; cs.why = ALI_SEQ_LIMIT; continue; }
                 const unsigned wi = cs.wi + (unsigned)(s == 0 ? -1 : s == 1 ? 1 : s == 2 ? -g.wnx : g.wnx);
+                // the neighbour's state in one go (independent loads; T is stored window-indexed like the rest:
+                // t[z * t_stride + x - toff] == t[wi] for every grid the march runs on)
                 const int32_t stv = g.st[wi];
+                const uint8_t cfv = g.cf[wi];
+                const double cvv = g.cv[wi];
+                const double told = g.t[wi];
                 if (stv != 0) {
                     const int nnz_l = (nnz_bug && s < 2 && stv > 0) ? nnx : nnz;
                     double v;
                     int fb = 0;
                     if (cs.miss_ready) { v = cs.miss_v; fb = cs.miss_fb; cs.miss_ready = 0; }
-                    else if (nnz_l == nnz && g.cf[wi]) v = g.cv[wi];
+                    else if (nnz_l == nnz && cfv) v = cvv;
                     else { cs.miss = 1; cs.mz = z; cs.mx = x; cs.mnnz = nnz_l; return 0; }
                     cnt.evals++;
                     cnt.fallbacks += fb;
-                    const bool changed = (stv == -1) || !(g.tt(z, x) == v);
-                    g.tref(z, x) = v;
+                    const bool changed = (stv == -1) || !(told == v);
+                    g.t[wi] = v;
                     if (changed) ali_seq_invalidate(g, z, x, wi);
                     if (nnz_l == nnz && !fb) { g.cv[wi] = v; g.cf[wi] = 1; }
                     else g.cf[wi] = 0;
@@ -480,6 +495,87 @@ ALI_DEV int ali_seq_march_coop(AliSeqGrid &g_mem, const AliModel &m, int cx, int
     cs.miss = 0; cs.mz = cs.mx = cs.mnnz = 0;
     cs.miss_ready = 0; cs.miss_fb = 0; cs.miss_v = 0.0;
     cs.finished = 0; cs.why = ALI_SEQ_EMPTY;
+#if defined(__CUDA_ARCH__)
+    if (nlanes > 32) {
+        // CTA of several warps: warp 0 is the walker (lane 0) and, when the walk stops at a miss, finds
+        // the step's candidates exactly as the one-warp form does; the candidates are then evaluated ONE
+        // PER WARP (a lone lane runs the update at single-thread latency, where 32 different nodes in
+        // one warp serialise their divergent paths), between two CTA barriers.
+        __shared__ int s_nc, s_done, s_serve, s_miss_fb;
+        __shared__ int s_cz[32], s_cx[32], s_cnnz[32];
+        __shared__ double s_miss_v;
+        const int warp = lane >> 5, wl = lane & 31, nw = nlanes >> 5;
+        if (lane == 0) s_done = 0;
+        for (;;) {
+            if (warp == 0) {
+                const int ntr = __shfl_sync(0xffffffffu, g.ntr, 0);
+                const int serve = __shfl_sync(0xffffffffu, cs.miss, 0);
+                const int pz = __shfl_sync(0xffffffffu, cs.iz, 0), px = __shfl_sync(0xffffffffu, cs.ix, 0);
+                const int ps = __shfl_sync(0xffffffffu, cs.s, 0);
+                const int mz = __shfl_sync(0xffffffffu, cs.mz, 0), mx = __shfl_sync(0xffffffffu, cs.mx, 0);
+                const int mnnz = __shfl_sync(0xffffffffu, cs.mnnz, 0);
+                bool has = false;
+                int cz_c = 0, cx_c = 0, cnnz = g.nz;
+                if (serve && wl == 0) { has = true; cz_c = mz; cx_c = mx; cnnz = mnnz; }
+                if (serve && wl >= 1 && wl <= 3) {
+                    const int d = ps + wl;
+                    if (d < 4) {
+                        cz_c = pz + (d == 2 ? -1 : d == 3 ? 1 : 0); cx_c = px + (d == 0 ? -1 : d == 1 ? 1 : 0);
+                        has = ali_coop_wanted_node(g, cz_c, cx_c);
+                    }
+                }
+                {
+                    const int slot = serve ? wl - 4 : wl;
+                    if (slot >= 0 && !has) {
+                        const int hp = 1 + (slot >> 2), dir = slot & 3;
+                        if (hp <= ntr) {
+                            const AliHeapEnt he = g.heap[hp];
+                            cz_c = ALI_ENT_Z(he) + (dir == 2 ? -1 : dir == 3 ? 1 : 0);
+                            cx_c = ALI_ENT_X(he) + (dir == 0 ? -1 : dir == 1 ? 1 : 0);
+                            has = ali_coop_wanted_node(g, cz_c, cx_c);
+                        }
+                    }
+                }
+                // two lanes may name the same node (neighbouring heap entries): keep the first
+                const unsigned long long key = ((unsigned long long)(unsigned)cz_c << 32) | (unsigned)cx_c;
+                const unsigned same = __match_any_sync(0xffffffffu, has ? key : (0xffffffff00000000ull | (unsigned)wl));
+                if (has && (same & ((1u << wl) - 1u))) has = false;
+                const unsigned mask = __ballot_sync(0xffffffffu, has);
+                if (has) {
+                    const int k = __popc(mask & ((1u << wl) - 1u));
+                    s_cz[k] = cz_c; s_cx[k] = cx_c; s_cnnz[k] = cnnz;
+                }
+                if (wl == 0) { s_nc = __popc(mask); s_serve = serve; }
+            }
+            __syncthreads();
+            if (s_done) break;
+            {
+                const int nc = s_nc, serve = s_serve;
+                const int k = warp + wl * nw;   // candidate k -> warp k % nw, lane k / nw
+                if (k < nc) {
+                    int fb = 0;
+                    const int cz_c = s_cz[k], cx_c = s_cx[k];
+                    const double v = ali_seq_eval(m, g, cz_c, cx_c, s_cnnz[k], &fb);
+                    if (k == 0 && serve) { s_miss_v = v; s_miss_fb = fb; }
+                    else if (!fb) { g.cv[g.widx(cz_c, cx_c)] = v; g.cf[g.widx(cz_c, cx_c)] = 1; }
+                }
+            }
+            __syncthreads();
+            if (lane == 0) {
+                if (cs.miss) { cs.miss_v = s_miss_v; cs.miss_fb = s_miss_fb; cs.miss_ready = 1; cs.miss = 0; }
+                cnt.steps++;
+                cnt.computed += s_nc;
+                s_done = ali_coop_advance(g, cs, cx, cz, max_dist, nnz_bug, stop_r, cnt);
+            }
+        }
+        g_mem.ntr = g.ntr; g_mem.overflow = g.overflow; g_mem.ndup = g.ndup;
+        g_mem.dup0 = g.dup0; g_mem.dup1 = g.dup1; g_mem.dup2 = g.dup2; g_mem.dup3 = g.dup3;
+        cnt_mem = cnt;
+        if (!cs.finished) cs.why = ALI_SEQ_EMPTY;
+        __syncthreads();   // (s_done is re-armed by the next march)
+        return cs.why;
+    }
+#endif
     for (;;) {
         int done = 0;
 #if defined(__CUDA_ARCH__)
@@ -574,6 +670,10 @@ ALI_DEV void ali_seq_clear(AliSeqGrid &g, bool clear_t, int lane, int nlanes)
             const unsigned long long nanbits = 0xFFFFFFFFFFFFFFFFull;
             memcpy(&g.t[i], &nanbits, sizeof(double));
         }
+    if (g.hkey) {
+        const size_t nk = ALI_HKEY_SLOTS(g.heap_cap);
+        for (size_t i = lane; i < nk; i += nlanes) g.hkey[i] = ALI_KEY_NONE;
+    }
     g.ntr = 0;
     g.overflow = 0;
     g.ndup = 0;
@@ -781,7 +881,7 @@ ALI_DEV void ali_src_level_fill(AliSrcState &s, const AliModel &m, const AliSour
     AliSeqGrid &g = s.lv[cur];
     ali_seq_clear(g, true, lane, nlanes);
     if (l == 0) {
-        if (sync_between) ALI_SYNCWARP();
+        if (sync_between) ALI_SYNCCTA();
         ali_seq_seed(g, m, s.base, p.isz, p.isx, s.cz[cur], s.cx[cur], ali_src_level_ring(p, 0),
                      p.fine ? 1.0 : -1.0, lane, nlanes);
     }
@@ -856,34 +956,39 @@ ALI_DEV void ali_seq_source(const AliModel &m, const AliSourcePlan &p, const Ali
         long long t0 = ALI_CLOCK();
         ali_src_level_geometry(s, m, p, sc, l);
         ali_src_level_fill(s, m, p, l, lane, nlanes, true);
-        ALI_SYNCWARP();
+        ALI_SYNCCTA();
         long long t1 = ALI_CLOCK();
         if (lane == 0) ali_src_level_start(s, p, l);
-        ALI_SYNCWARP();
+        ALI_SYNCCTA();
         s.cnt.cyc_fill += t1 - t0;
         s.cnt.cyc_start += ALI_CLOCK() - t1;
         if (coop) ali_src_level_seq_coop(s, m, p, l, lane, nlanes);
         else if (lane == 0) ali_src_level_seq(s, m, p, l, -1);
-        ALI_SYNCWARP();
+        ALI_SYNCCTA();
     }
     ali_src_main_geometry(s, m, p, sc);
 #if defined(__CUDA_ARCH__)
-    s.overflow = __shfl_sync(0xffffffffu, s.overflow, 0);
+    {   // thread 0's verdict for everybody
+        __shared__ int s_ovf;
+        if (lane == 0) s_ovf = s.overflow;
+        __syncthreads();
+        s.overflow = s_ovf;
+    }
 #endif
     if (!s.overflow) {
         long long t0 = ALI_CLOCK();
         ali_seq_clear(s.mg, true, lane, nlanes);
-        ALI_SYNCWARP();
+        ALI_SYNCCTA();
         long long t1 = ALI_CLOCK();
         const int last = (p.nlev - 1) & 1;
         if (lane == 0) ali_seq_handoff(s.lv[last], s.cz[last], s.cx[last], s.mg, p.isz, p.isx);
-        ALI_SYNCWARP();
+        ALI_SYNCCTA();
         s.cnt.cyc_fill += t1 - t0;
         s.cnt.cyc_start += ALI_CLOCK() - t1;
         if (coop) ali_seq_march_coop(s.mg, m, p.isx, p.isz, -1, 0, p.stop_r, s.cnt, lane, nlanes);
         else if (lane == 0) ali_seq_march(s.mg, m, p.isx, p.isz, -1, 0, p.stop_r, s.cnt);
         s.overflow |= s.mg.overflow;
-        ALI_SYNCWARP();
+        ALI_SYNCCTA();
     }
     s.cnt.cyc_total = ALI_CLOCK() - t_begin;
     res.wz0 = s.mg.wz0; res.wx0 = s.mg.wx0; res.wnz = s.mg.wnz; res.wnx = s.mg.wnx;

@@ -113,7 +113,11 @@ __global__ void ali_vmax_kernel(AliModel m, unsigned long long *out_bits)
     if ((threadIdx.x & 31) == 0) atomicMax(out_bits, (unsigned long long)__double_as_longlong(best));
 }
 
-__global__ void __launch_bounds__(32, 1) ali_seq_kernel(AliBatch b)
+// One CTA per source: thread 0 walks the reference's heap loop, warp 0 finds the evaluations worth doing
+// ahead, and every warp evaluates one of them per step (ali_seq_march_coop).  With blockDim.x == 32 the
+// one-warp form of round 1 runs instead.
+#define ALI_SEQ_MAX_THREADS 256
+__global__ void __launch_bounds__(ALI_SEQ_MAX_THREADS, 1) ali_seq_kernel(AliBatch b)
 {
     const int src = blockIdx.x;
     const int lane = threadIdx.x;
@@ -126,13 +130,13 @@ __global__ void __launch_bounds__(32, 1) ali_seq_kernel(AliBatch b)
     sc.sA = b.seq_s + (size_t)src * 2 * b.seq_cap;
     sc.sB = sc.sA + b.seq_cap;
     sc.heap = reinterpret_cast<AliHeapEnt *>(b.seq_heap) + (size_t)src * b.heap_cap;
-    sc.hkey = b.seq_hkey + (size_t)src * b.heap_cap;
+    sc.hkey = b.seq_hkey + (size_t)src * ALI_HKEY_SLOTS(b.heap_cap);
     sc.cval = b.seq_cval + (size_t)src * b.seq_cap;
     sc.cflag = b.seq_cflag + (size_t)src * b.seq_cap;
     sc.heap_cap = b.heap_cap;
     sc.status_cap = b.seq_cap;
     AliSeqResult res;
-    ali_seq_source(b.m, p, sc, res, lane, 32);
+    ali_seq_source(b.m, p, sc, res, lane, (int)blockDim.x);
     if (lane == 0) {
         rec.seq = res;
         rec.overflow = res.overflow ? 1 : 0;
@@ -542,6 +546,338 @@ __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
     }
 }
 
+// ---------------------------------------------------------------------------
+// The same march with a thread-block CLUSTER per source (2, 4 or 8 CTAs = SMs): for batches with
+// fewer sources than SMs (128 sources sharded over several GPUs leave 9 SMs per source on each).
+// Every CTA works on a slice of the source's band list each phase; the three barriers of a round
+// become cluster barriers (barrier.cluster arrive.release / wait.acquire, which also invalidates
+// L1, so plain loads after it see the other CTAs' stores).  Everything the CTAs share lives in
+// global memory (L2: 234-262 cycles, the same as a remote shared-memory access on this part):
+// the band lists and their values as before, and a small control block per source -- list
+// counters, the round's minima, the window-change bitmap and the sort bins -- touched only with
+// atomics and volatile loads.  The set of nodes evaluated, published, accepted and enlisted in a
+// round does not depend on how the lists are split, so the field is bit-identical to the
+// one-CTA kernel's (tests/test_gpu_parity.py::test_cluster_march_equals_single_cta).
+struct AliClusterCtl {
+    int count[2], nwork[2];
+    unsigned long long evalmin[2], basemin[2];
+    int force[2];
+    int overflow, pad;
+    int bins[ALI_SORT_BINS];
+    unsigned dmap[ALI_DMAP_WORDS];
+};
+
+__device__ __forceinline__ int ali_ldv(const int *p) { return *(const volatile int *)p; }
+__device__ __forceinline__ unsigned long long ali_ldv(const unsigned long long *p) { return *(const volatile unsigned long long *)p; }
+__device__ __forceinline__ bool ali_dmap_test_g(const unsigned *dmap, int iz, int ix)
+{
+    const unsigned m = (1u << ALI_DMAP_BITS) - 1u;
+    const unsigned xs = (unsigned)ix & m;
+    return (*(const volatile unsigned *)&dmap[(((unsigned)iz & m) << (ALI_DMAP_BITS - 5)) | (xs >> 5)] >> (xs & 31u)) & 1u;
+}
+
+__device__ __forceinline__ void ali_cluster_sync()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned ali_cluster_rank()
+{
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ unsigned ali_cluster_size()
+{
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) ali_march_cluster_kernel(AliBatch b, AliClusterCtl *ctl_all)
+{
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    double *s_sincos = reinterpret_cast<double *>(s_raw);
+    const int C = (int)ali_cluster_size(), rank = (int)ali_cluster_rank();
+    const int src = blockIdx.x / C;
+    const int tid = threadIdx.x, gtid = rank * NT + tid, GT = C * NT;
+    AliSourceRec &rec = b.rec[src];
+    AliClusterCtl *ctl = ctl_all + src;
+    __shared__ unsigned long long s_evals, s_fbs;
+    __shared__ AliBandGrid s_grid;   // copy for the out-of-line FD fallback
+    __shared__ int s_wsum[32];
+    __shared__ long long s_cyc[4], s_tprev;
+    const int isz = (b.sg > 1 ? b.sg : 1) * rec.src_iz, isx = (b.sg > 1 ? b.sg : 1) * rec.src_ix;
+
+    AliBandGrid g;
+    g.nz = b.nz; g.nx = b.nx;
+    g.T = b.Tt + (size_t)src * b.tn;
+    g.st = b.st + (size_t)src * b.tn;
+    g.t4x = (b.nx + 3) >> 2;
+    g.dirty = nullptr;
+    g.tiles_x = 0;
+    g.dnx = b.m.dnx;
+    g.mv = ali_band_view(b.sg);
+
+    const int cap = b.band_cap;
+    double *val0 = b.stage + (size_t)src * 2 * cap, *val1 = val0 + cap;
+    unsigned *ent0 = b.lists + (size_t)src * 4 * cap, *ent1 = ent0 + cap, *wrk0 = ent1 + cap, *wrk1 = wrk0 + cap;
+
+    for (int q = tid; q < 404 * 4; q += NT) s_sincos[q] = ali_cr_sincos_tab[q];
+    if (tid == 0) {
+        s_grid = g;
+        s_evals = 0; s_fbs = 0;
+        s_cyc[0] = s_cyc[1] = s_cyc[2] = s_cyc[3] = 0;
+    }
+    if (rec.overflow) return;   // (the sequential phase's verdict: the same for every CTA of the cluster)
+    if (gtid == 0) {            // the control block arrives zeroed (host memset)
+        ctl->evalmin[0] = ~0ull; ctl->evalmin[1] = ~0ull; ctl->basemin[0] = ~0ull; ctl->basemin[1] = ~0ull;
+    }
+    ali_cluster_sync();
+
+    // hand-over of the sequential phase's window (see ali_march_kernel), shared by the CTAs
+    {
+        const AliSeqResult w = rec.seq;
+        const int nlev = b.sg > 1 ? 2 : 3;
+        const size_t woff = (size_t)src * 2 * b.seq_cap + ((((nlev - 1) & 1) == 0) ? b.seq_cap : 0);
+        const int32_t *wst = b.seq_s + woff;
+        const double *wt = b.seq_t + woff;
+        const int wn = w.wnz * w.wnx;
+        for (int base = rank * NT; base < wn; base += GT) {
+            int i = base + tid;
+            int k = 0;
+            unsigned entry = 0;
+            double tv = 0.0;
+            if (i < wn) {
+                int z = i / w.wnx, x = i - z * w.wnx;
+                int32_t s = wst[i];
+                if (s >= 0) {
+                    tv = wt[i];
+                    const size_t node = g.ti(w.wz0 + z, w.wx0 + x);
+                    g.T[node] = tv;
+                    if (s == 0) g.st[node] = ALI_ST_ALIVE;
+                    else { k = 1; entry = ALI_PACK(w.wz0 + z, w.wx0 + x); }
+                }
+            }
+            int pos = ali_warp_reserve(k, &ctl->count[0]);
+            if (k) {
+                if (pos < cap) { ent0[pos] = entry; wrk0[pos] = (unsigned)pos; val0[pos] = tv; }
+                else ctl->overflow = 2;
+            }
+        }
+    }
+    ali_cluster_sync();
+    if (gtid == 0) ctl->nwork[0] = ali_ldv(&ctl->count[0]);
+    ali_cluster_sync();
+
+    int rounds = 0, max_band = 0;
+    unsigned my_evals = 0, my_fbs = 0;
+    int cur = 0;
+    while (true) {
+        // (read after a cluster barrier, not written before the next one: the same for every thread of the cluster)
+        const int n = ali_ldv(&ctl->count[cur]);
+        if (n == 0 || ali_ldv(&ctl->overflow)) break;
+        const int nwork = ali_ldv(&ctl->nwork[cur]);
+        double *val = cur == 0 ? val0 : val1, *nval = cur == 0 ? val1 : val0;
+        unsigned *ent = cur == 0 ? ent0 : ent1, *nent = cur == 0 ? ent1 : ent0;
+        unsigned *wrk = cur == 0 ? wrk0 : wrk1, *nwrk = cur == 0 ? wrk1 : wrk0;
+        rounds++;
+        if (n > max_band) max_band = n;
+        if (tid == 0) s_tprev = clock64();
+        const bool resort = b.resort_every > 0 && (rounds % b.resort_every) == 0;
+        // phase A
+        if (gtid == 0) { ctl->count[cur ^ 1] = 0; ctl->nwork[cur ^ 1] = 0; ctl->basemin[cur ^ 1] = ~0ull; ctl->evalmin[cur ^ 1] = ~0ull; }
+        for (int q = gtid; q < ALI_DMAP_WORDS / 4; q += GT) reinterpret_cast<uint4 *>(ctl->dmap)[q] = make_uint4(0u, 0u, 0u, 0u);
+        if (resort)
+            for (int q = gtid; q < ALI_SORT_BINS; q += GT) ctl->bins[q] = 0;
+        double lmin = 1e300;
+        unsigned pe0 = 0, pe1 = 0;
+        double pv0 = 0.0, pv1 = 0.0;
+        int pmask = 0, it = 0;
+        // (warp w of CTA r takes the items of warp slot w * C + r: every CTA of the cluster gets the same
+        // number of warps' worth of work, also when the list is shorter than the cluster has threads)
+        const int q0 = (((tid >> 5) * C + rank) << 5) | (tid & 31);
+        for (int q = q0; q < nwork; q += GT, it++) {
+            const int i = (int)wrk[q];
+            const unsigned e = ent[i];
+            const int iz = ALI_PACK_Z(e), ix = ALI_PACK_X(e);
+            int fb = 0;
+            const double vold = val[i];
+            double v = ali_band_eval(b.m, b.m_dev, g, &s_grid, iz, ix, &fb, s_sincos);
+            if (v != v) v = __longlong_as_double(ALI_T_NAN_VALUE_BITS);
+            val[i] = v;
+            my_evals++;
+            my_fbs += fb;
+            lmin = fmin(lmin, v);
+            if (it == 0) { pe0 = e; pv0 = v; pmask |= (v != vold ? 1 : 0) | (fb ? 4 : 0); }
+            else if (it == 1) { pe1 = e; pv1 = v; pmask |= (v != vold ? 2 : 0) | (fb ? 8 : 0); }
+            else {
+                if (v != vold) val[i] = -v;
+                if (fb) ctl->force[rounds & 1] = 1;
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) lmin = fmin(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+        if ((tid & 31) == 0 && lmin < 1e300)
+            atomicMin(&ctl->evalmin[cur], (unsigned long long)__double_as_longlong(lmin));
+        ali_cluster_sync();
+        if (tid == 0) { const long long now = clock64(); s_cyc[0] += now - s_tprev; s_tprev = now; }
+        // phase B
+        if (gtid == 0) ctl->force[(rounds + 1) & 1] = 0;
+        if (pmask & 1) { g.T[g.ti(ALI_PACK_Z(pe0), ALI_PACK_X(pe0))] = pv0; ali_dmap_mark(ctl->dmap, ALI_PACK_Z(pe0), ALI_PACK_X(pe0)); }
+        if (pmask & 2) { g.T[g.ti(ALI_PACK_Z(pe1), ALI_PACK_X(pe1))] = pv1; ali_dmap_mark(ctl->dmap, ALI_PACK_Z(pe1), ALI_PACK_X(pe1)); }
+        if (pmask & 4) ali_dmap_row(ctl->dmap, ALI_PACK_Z(pe0), ALI_PACK_X(pe0), 1u);
+        if (pmask & 8) ali_dmap_row(ctl->dmap, ALI_PACK_Z(pe1), ALI_PACK_X(pe1), 1u);
+        for (int q = q0 + 2 * GT; q < nwork; q += GT) {
+            const int i = (int)wrk[q];
+            const unsigned e = ent[i];
+            const double v = val[i];
+            if (v < 0.0) {
+                val[i] = -v;
+                g.T[g.ti(ALI_PACK_Z(e), ALI_PACK_X(e))] = -v;
+                ali_dmap_mark(ctl->dmap, ALI_PACK_Z(e), ALI_PACK_X(e));
+            }
+        }
+        ali_cluster_sync();
+        if (tid == 0) { const long long now = clock64(); s_cyc[1] += now - s_tprev; s_tprev = now; }
+        // phase C
+        const int force = ali_ldv(&ctl->force[rounds & 1]);
+        const unsigned long long em = ali_ldv(&ctl->evalmin[cur]), bmn = ali_ldv(&ctl->basemin[cur]);
+        const double thr = __longlong_as_double((long long)(em < bmn ? em : bmn)) + b.delta;
+        double bmin = 1e300;
+        for (int i = q0; i - (tid & 31) < n; i += GT) {   // (whole warps stay in the loop: the reservation shuffles)
+            int k = 0, kw = 0;
+            unsigned out[4];
+            double v = 0.0;
+            if (i < n) {
+                const unsigned e = ent[i];
+                v = val[i];
+                const int iz = ALI_PACK_Z(e), ix = ALI_PACK_X(e);
+                if (!(v > thr)) {
+                    k = ali_band_accept(g, iz, ix, out);
+                    kw = k;
+                    v = 0.0;
+                } else {
+                    out[0] = e; k = 1;
+                    if (!resort) {
+                        if (force || ali_dmap_test_g(ctl->dmap, iz, ix)) kw = 1;
+                        else bmin = fmin(bmin, v);
+                    }
+                }
+            }
+            int pos, wpos;
+            ali_warp_reserve2(k, kw, &ctl->count[cur ^ 1], &ctl->nwork[cur ^ 1], pos, wpos);
+            if (pos + k <= cap) {
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (q < k) {
+                        nent[pos + q] = out[q];
+                        nval[pos + q] = v;
+                        if (q < kw) nwrk[wpos + q] = (unsigned)(pos + q);
+                    }
+            } else if (k) {
+                ctl->overflow = 2;
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) bmin = fmin(bmin, __shfl_xor_sync(0xffffffffu, bmin, o));
+        if ((tid & 31) == 0 && bmin < 1e300)
+            atomicMin(&ctl->basemin[cur ^ 1], (unsigned long long)__double_as_longlong(bmin));
+        ali_cluster_sync();
+        if (tid == 0) { const long long now = clock64(); s_cyc[2] += now - s_tprev; s_tprev = now; }
+        if (resort && !ali_ldv(&ctl->overflow)) {
+            // counting sort of the new list by angular bin through the shared bins: histogram (every
+            // CTA), exclusive scan (CTA 0), scatter back into the current buffers, work list + base minimum
+            const int nn = ali_ldv(&ctl->count[cur ^ 1]);
+            for (int i = gtid; i < nn; i += GT) atomicAdd(&ctl->bins[ali_sort_bin(nent[i], isz, isx)], 1);
+            ali_cluster_sync();
+            if (rank == 0) {
+                constexpr int PER = (ALI_SORT_BINS + NT - 1) / NT;
+                int loc[PER];
+                int sum = 0;
+#pragma unroll
+                for (int q = 0; q < PER; q++) {
+                    int idx = tid * PER + q;
+                    loc[q] = idx < ALI_SORT_BINS ? ali_ldv(&ctl->bins[idx]) : 0;
+                    sum += loc[q];
+                }
+                int incl = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    int v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if ((tid & 31) >= o) incl += v;
+                }
+                if ((tid & 31) == 31) s_wsum[tid >> 5] = incl;
+                __syncthreads();
+                if (tid < 32) {
+                    int w = tid < NT / 32 ? s_wsum[tid] : 0;
+                    int wi = w;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        int v = __shfl_up_sync(0xffffffffu, wi, o);
+                        if (tid >= o) wi += v;
+                    }
+                    s_wsum[tid] = wi - w;
+                }
+                __syncthreads();
+                int run = s_wsum[tid >> 5] + incl - sum;
+#pragma unroll
+                for (int q = 0; q < PER; q++) {
+                    int idx = tid * PER + q;
+                    if (idx < ALI_SORT_BINS) ctl->bins[idx] = run;
+                    run += loc[q];
+                }
+                if (tid == 0) { ctl->nwork[cur] = 0; ctl->basemin[cur] = ~0ull; }
+            }
+            ali_cluster_sync();
+            for (int i = gtid; i < nn; i += GT) {
+                const unsigned e = nent[i];
+                const int pos = atomicAdd(&ctl->bins[ali_sort_bin(e, isz, isx)], 1);
+                ent[pos] = e;
+                val[pos] = nval[i];
+            }
+            ali_cluster_sync();
+            double bm = 1e300;
+            for (int i = q0; i - (tid & 31) < nn; i += GT) {
+                int kw = 0;
+                if (i < nn) {
+                    const unsigned e = ent[i];
+                    const double v = val[i];
+                    if (v == 0.0) kw = 1;
+                    else {
+                        if (force || ali_dmap_test_g(ctl->dmap, ALI_PACK_Z(e), ALI_PACK_X(e))) kw = 1;
+                        else bm = fmin(bm, v);
+                    }
+                }
+                int wpos = ali_warp_reserve(kw, &ctl->nwork[cur]);
+                if (kw) wrk[wpos] = (unsigned)i;
+            }
+            for (int o = 16; o > 0; o >>= 1) bm = fmin(bm, __shfl_xor_sync(0xffffffffu, bm, o));
+            if ((tid & 31) == 0 && bm < 1e300)
+                atomicMin(&ctl->basemin[cur], (unsigned long long)__double_as_longlong(bm));
+            if (gtid == 0) { ctl->count[cur] = nn; ctl->evalmin[cur] = ~0ull; }
+            ali_cluster_sync();
+        } else {
+            cur ^= 1;
+        }
+        if (tid == 0) {
+            const long long now = clock64(); s_cyc[3] += now - s_tprev;
+        }
+    }
+    atomicAdd(&s_evals, (unsigned long long)my_evals);
+    atomicAdd(&s_fbs, (unsigned long long)my_fbs);
+    __syncthreads();
+    if (tid == 0) {
+        atomicAdd((unsigned long long *)&rec.band_evals, s_evals);
+        atomicAdd((unsigned long long *)&rec.band_fallbacks, s_fbs);
+        if (rank == 0) {
+            rec.rounds = rounds;
+            rec.max_band = max_band;
+            for (int q = 0; q < 4; q++) rec.cycles[q] = s_cyc[q];
+            const int ovf = ali_ldv(&ctl->overflow);
+            if (ovf) rec.overflow = ovf;
+        }
+    }
+}
+
 // Tiled march field -> the caller's row-major field, T / subgrid (ATR:2832); nodes the march never
 // reached get the reference's 0.  A warp reads 8 sectors of 8 tiles and writes 256 contiguous bytes;
 // the other three rows of those tiles are read by the next rows' warps out of L2.
@@ -555,7 +891,7 @@ __global__ void ali_finalize_kernel(const double *Tt, const uint8_t *st, double 
         const size_t node = src * tn + ((((size_t)(z >> 2) * t4x + (size_t)(x >> 2)) << 4) | (size_t)(((z & 3) << 2) | (x & 3)));
         const double v = Tt[node];
         // an accepted node without a number (NaN material / velocity) stays NaN, as in the reference
-        T[i] = (v >= 0.0) ? v / sg : ((v != v && __double_as_longlong(v) == ALI_T_NAN_VALUE_BITS && st[node] == ALI_ST_ALIVE) ? v : 0.0);
+        T[i] = (v >= 0.0) ? v / sg : ((v != v && st[node] == ALI_ST_ALIVE) ? __longlong_as_double(ALI_T_NAN_VALUE_BITS) : 0.0);
     }
 }
 
@@ -796,9 +1132,12 @@ struct alifmm_ctx {
     int threads_per_source = 768;   // 80 registers per thread: fewer spills than 1024 x 64, more warps than 512 x 128 (measured)
     int resort_every = 8;
     int band_smem_bytes = 0;   // measured on B200: L1 for the T / status gathers is worth more than smem lists
+    int seq_threads = 32;      // CTA size of the sequential near-source kernel: 32 = one warp (measured fastest); 64..256 = one candidate per warp
+    int cluster_size = 0;      // CTAs (SMs) per source in the band march: 0 = as many (1, 2, 4, 8) as keep the batch in one wave
+    int cluster_threads = 0;   // CTA size of the cluster march: 0 = 512 (128 registers, no spills), else 512 or 768
     // resident batch
     int n_slots = 0, sg = 0, fz = 0, fx = 0;
-    DevBuf T, Tt, st, seq_t, seq_s, seq_heap, seq_hkey, seq_cval, seq_cflag, lists, stage, rec, jobs, ray_x, ray_y, ray_time, ray_len, ray_flag, ray_off, pack, misc;
+    DevBuf T, Tt, st, seq_t, seq_s, seq_heap, seq_hkey, seq_cval, seq_cflag, lists, stage, rec, jobs, ray_x, ray_y, ray_time, ray_len, ray_flag, ray_off, pack, misc, ctl;
     alifmm_counters_t cnt{};
 };
 
@@ -1012,7 +1351,7 @@ extern "C" void alifmm_destroy(alifmm_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (DevBuf &mb : c->model_allocs) dev_release(mb, c->device);
     DevBuf *bufs[] = {&c->T, &c->Tt, &c->st, &c->seq_t, &c->seq_s, &c->seq_heap, &c->seq_hkey, &c->seq_cval, &c->seq_cflag, &c->lists, &c->stage, &c->rec, &c->jobs,
-                      &c->ray_x, &c->ray_y, &c->ray_time, &c->ray_len, &c->ray_flag, &c->ray_off, &c->pack, &c->misc};
+                      &c->ray_x, &c->ray_y, &c->ray_time, &c->ray_len, &c->ray_flag, &c->ray_off, &c->pack, &c->misc, &c->ctl};
     for (DevBuf *b : bufs) dev_release(*b, c->device);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -1136,6 +1475,18 @@ extern "C" int alifmm_set_option(alifmm_ctx *c, const char *name, double value)
     } else if (!strcmp(name, "resort_every")) {
         if (value < 0 || value > 1000000) return fail(ALIFMM_E_INVALID, "resort_every must be >= 0");
         c->resort_every = (int)value;
+    } else if (!strcmp(name, "seq_threads")) {
+        int t = (int)value;
+        if (t != 32 && t != 64 && t != 128 && t != 256) return fail(ALIFMM_E_INVALID, "seq_threads must be 32, 64, 128 or 256");
+        c->seq_threads = t;
+    } else if (!strcmp(name, "cluster_size")) {
+        int t = (int)value;
+        if (t != 0 && t != 1 && t != 2 && t != 4 && t != 8) return fail(ALIFMM_E_INVALID, "cluster_size must be 0 (auto), 1, 2, 4 or 8");
+        c->cluster_size = t;
+    } else if (!strcmp(name, "cluster_threads")) {
+        int t = (int)value;
+        if (t != 0 && t != 512 && t != 768) return fail(ALIFMM_E_INVALID, "cluster_threads must be 0 (auto), 512 or 768");
+        c->cluster_threads = t;
     } else if (!strcmp(name, "band_smem_kb")) {
         if (value < 0 || value > 180) return fail(ALIFMM_E_INVALID, "band_smem_kb must be in [0, 180]");
         c->band_smem_bytes = (int)value * 1024;
@@ -1208,7 +1559,7 @@ static int ttf_attempt(alifmm_ctx *c, int32_t n_src, const int32_t *src_iz, cons
     if ((rc = dev_reserve(c->seq_t, (size_t)n_src * 2 * b.seq_cap * sizeof(double))) != 0) return rc;
     if ((rc = dev_reserve(c->seq_s, (size_t)n_src * 2 * b.seq_cap * sizeof(int32_t))) != 0) return rc;
     if ((rc = dev_reserve(c->seq_heap, (size_t)n_src * 2 * b.heap_cap * sizeof(int32_t))) != 0) return rc;
-    if ((rc = dev_reserve(c->seq_hkey, (size_t)n_src * b.heap_cap * sizeof(double))) != 0) return rc;
+    if ((rc = dev_reserve(c->seq_hkey, (size_t)n_src * ALI_HKEY_SLOTS(b.heap_cap) * sizeof(double))) != 0) return rc;
     if ((rc = dev_reserve(c->seq_cval, (size_t)n_src * b.seq_cap * sizeof(double))) != 0) return rc;
     if ((rc = dev_reserve(c->seq_cflag, (size_t)n_src * b.seq_cap + 16)) != 0) return rc;
     if ((rc = dev_reserve(c->lists, (size_t)n_src * 4 * b.band_cap * sizeof(unsigned))) != 0) return rc;
@@ -1228,10 +1579,48 @@ static int ttf_attempt(alifmm_ctx *c, int32_t n_src, const int32_t *src_iz, cons
     CUDA_TRY(cudaEventRecord(c->ev[0], s));
     CUDA_TRY(cudaMemsetAsync(b.Tt, ALI_T_UNSET_BYTE, (size_t)n_src * b.tn * sizeof(double), s)); // NaN = far
     CUDA_TRY(cudaMemsetAsync(b.st, 0, (size_t)n_src * b.tn, s));
-    ali_seq_kernel<<<n_src, 32, 0, s>>>(b);
+    ali_seq_kernel<<<n_src, c->seq_threads, 0, s>>>(b);
+    c->cnt.seq_threads = c->seq_threads;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(c->ev[1], s));
+    // CTAs per source: a cluster when the batch leaves SMs idle (sources sharded over several GPUs)
+    int csize = 1, cthreads = c->cluster_threads ? c->cluster_threads : 512;
     {
+        const size_t csmem = (size_t)404 * 4 * 8;
+        for (int cand : {8, 4, 2}) {
+            if (c->cluster_size != 0 && c->cluster_size != cand) continue;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(n_src * cand)); cfg.blockDim = dim3((unsigned)cthreads); cfg.dynamicSmemBytes = csmem;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = (unsigned)cand; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            int nclusters = 0;
+            cudaError_t qe = cthreads == 768 ? cudaOccupancyMaxActiveClusters(&nclusters, ali_march_cluster_kernel<768>, &cfg)
+                                             : cudaOccupancyMaxActiveClusters(&nclusters, ali_march_cluster_kernel<512>, &cfg);
+            if (qe != cudaSuccess) { cudaGetLastError(); continue; }
+            if (getenv("ALIFMM_DEBUG")) fprintf(stderr, "[alifmm] clusters of %d x %d threads resident at once: %d (batch: %d sources)\n", cand, cthreads, nclusters, n_src);
+            // automatic choice: every source's cluster resident at once (a second wave would double the time)
+            if (nclusters >= n_src || (c->cluster_size == cand && nclusters > 0)) { csize = cand; break; }
+        }
+        if (c->cluster_size == 1) csize = 1;
+    }
+    c->cnt.cluster_size = csize;
+    if (csize > 1) {
+        int rc2;
+        if ((rc2 = dev_reserve(c->ctl, (size_t)n_src * sizeof(AliClusterCtl))) != 0) return rc2;
+        CUDA_TRY(cudaMemsetAsync(c->ctl.p, 0, (size_t)n_src * sizeof(AliClusterCtl), s));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(n_src * csize)); cfg.blockDim = dim3((unsigned)cthreads);
+        cfg.dynamicSmemBytes = (size_t)404 * 4 * 8; cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)csize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        AliClusterCtl *ctlp = (AliClusterCtl *)c->ctl.p;
+        if (cthreads == 768) CUDA_TRY(cudaLaunchKernelEx(&cfg, ali_march_cluster_kernel<768>, b, ctlp));
+        else CUDA_TRY(cudaLaunchKernelEx(&cfg, ali_march_cluster_kernel<512>, b, ctlp));
+    } else {
         // band entries + work lists in shared memory when they fit in c->band_smem_bytes
         size_t need = (size_t)b.band_cap * 16;
         int smem_cap = need <= (size_t)c->band_smem_bytes ? b.band_cap : 0;
@@ -1280,7 +1669,15 @@ static int ttf_attempt(alifmm_ctx *c, int32_t n_src, const int32_t *src_iz, cons
     cn.kernel_launches = launches;
     cn.delta = b.delta;
     int overflow = 0;
+    cn.seq_mcycles_min = cn.march_mcycles_min = 1e300;
+    cn.seq_mcycles_max = cn.march_mcycles_max = 0.0;
     for (const AliSourceRec &r : recs) {
+        const double sc = 1e-6 * (double)r.seq.cnt.cyc_total;
+        const double mc = 1e-6 * (double)(r.cycles[0] + r.cycles[1] + r.cycles[2] + r.cycles[3]);
+        if (sc < cn.seq_mcycles_min) cn.seq_mcycles_min = sc;
+        if (sc > cn.seq_mcycles_max) cn.seq_mcycles_max = sc;
+        if (mc < cn.march_mcycles_min) cn.march_mcycles_min = mc;
+        if (mc > cn.march_mcycles_max) cn.march_mcycles_max = mc;
         cn.seq_pops += r.seq.cnt.pops;
         cn.seq_evals += r.seq.cnt.evals;
         cn.fallback_evals += r.seq.cnt.fallbacks + r.band_fallbacks;

@@ -69,6 +69,12 @@ typedef struct {
     double ms_rays;
     double vmax;              /* model-wide phase-velocity bound used for delta */
     double delta;             /* acceptance band of the last field batch, seconds */
+    int64_t cluster_size;     /* CTAs (SMs) per source in the band march of the last batch */
+    int64_t seq_threads;      /* threads per source in the sequential near-source phase */
+    double seq_mcycles_min;   /* fastest / slowest source of the last batch, SM cycles x 1e6: */
+    double seq_mcycles_max;   /*   sequential phase */
+    double march_mcycles_min; /*   band march (sum of its phases) */
+    double march_mcycles_max;
 } alifmm_counters_t;
 
 /* Number of CUDA devices visible to the process (0 when there is none). */
@@ -85,7 +91,11 @@ void alifmm_destroy(alifmm_ctx *ctx);
  * refined source box, default 27), "band_capacity_factor" (narrow-band list capacity as
  * a multiple of nz+nx of the solved grid, default 6), "threads_per_source" (CTA size of
  * the band march: 256, 512, 640, 768, 896 or 1024; default 768 = 80 registers per thread, measured
- * fastest on B200), "band_smem_kb" (shared memory for the band lists, 0..180, default 0 = keep L1
+ * fastest on B200), "cluster_size" (CTAs = SMs per source in the band march: 0 = automatic, the largest of
+ * 8 / 4 / 2 / 1 that keeps every source of the batch resident at once; results do not depend on it),
+ * "cluster_threads" (CTA size of the cluster march, 512 or 768), "seq_threads" (CTA size of the sequential
+ * near-source kernel: 32 = one warp per source, the default and measured fastest; 64, 128 or 256 evaluate one
+ * speculated node per warp between two CTA barriers -- same result, ~8 % slower on B200), "band_smem_kb" (shared memory for the band lists, 0..180, default 0 = keep L1
  * for the field gathers), "resort_every" (re-order the band
  * list along the front every this many rounds so that warps coalesce, default 8; 0 = never). */
 int alifmm_set_option(alifmm_ctx *ctx, const char *name, double value);

@@ -231,7 +231,7 @@ extern "C" int emu_ttf(int nz, int nx, const double *veln, const int32_t *velpn,
     AliSeqScratch sc;
     sc.tA = tA.data(); sc.tB = tB.data(); sc.sA = sA.data(); sc.sB = sB.data();
     sc.heap = reinterpret_cast<AliHeapEnt *>(heap.data()); sc.heap_cap = (int)(cap / 2 + 64); sc.status_cap = cap;
-    std::vector<double> hkey(cap / 2 + 64);
+    std::vector<double> hkey(ALI_HKEY_SLOTS(cap / 2 + 64));
     sc.hkey = hkey.data();
     std::vector<double> cval(g_coop_lanes > 0 ? cap : 0);
     std::vector<uint8_t> cflag(g_coop_lanes > 0 ? cap : 0);

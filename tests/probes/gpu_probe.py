@@ -22,6 +22,9 @@ ap.add_argument("--rays", type=int, default=0)
 ap.add_argument("--reps", type=int, default=1)
 ap.add_argument("--smemkb", type=int, default=-1)
 ap.add_argument("--resort", type=int, default=-1)
+ap.add_argument("--cluster", type=int, default=-1)
+ap.add_argument("--cthreads", type=int, default=-1)
+ap.add_argument("--seqthreads", type=int, default=-1)
 a = ap.parse_args()
 
 w = models.weld()
@@ -36,12 +39,16 @@ ctx = _capi.Context(w["veln"], w["velpn"], w["vel_map"], w["stif_den"], True, g,
 ctx.set_option("delta_frac", a.frac); ctx.set_option("handover_margin", a.margin); ctx.set_option("threads_per_source", a.threads)
 if a.smemkb >= 0: ctx.set_option("band_smem_kb", a.smemkb)
 if a.resort >= 0: ctx.set_option("resort_every", a.resort)
+if a.cluster >= 0: ctx.set_option("cluster_size", a.cluster)
+if a.cthreads >= 0: ctx.set_option("cluster_threads", a.cthreads)
+if a.seqthreads >= 0: ctx.set_option("seq_threads", a.seqthreads)
 print("create %.3f s, mem" % (time.time() - t0), ctx.mem_info())
 for rep in range(a.reps):
     t0 = time.time()
     ctx.ttf(iz, ix, a.sg, fetch=False)
     dt = time.time() - t0
     c = ctx.counters()
+    print("cluster %d | seq Mcyc %.0f..%.0f march Mcyc %.0f..%.0f" % (c["cluster_size"], c["seq_mcycles_min"], c["seq_mcycles_max"], c["march_mcycles_min"], c["march_mcycles_max"]))
     print("ttf wall %.3f s: seq %.1f ms march %.1f ms fin %.1f ms | node_solves %.3e -> %.3e /s | seq_pops %d band_rounds_max %d band_evals %.3e (%.2f/node) max_band %d fallbacks %d" % (
         dt, c["ms_seq"], c["ms_march"], c["ms_finalize"], c["node_solves"], c["node_solves"] / dt, c["seq_pops"], c["band_rounds_max"],
         c["band_evals"], c["band_evals"] / c["node_solves"], c["max_band"], c["fallback_evals"]), flush=True)
