@@ -122,7 +122,7 @@ ALI_DEV_NOINLINE double ali_band_fouds_slow(const AliModel *m_dev, const AliBand
 
 // Phase A: value the reference would store for this node given the current state.
 ALI_DEV double ali_band_eval(const AliModel &m, const AliModel *m_dev, const AliBandGrid &g,
-                             const AliBandGrid *g_mem, int iz, int ix, int *fallback, const double *sincos_tab = nullptr,
+                             const AliBandGrid *g_mem, int iz, int ix, int *fallback, const uint64_t *mt = nullptr,
                              bool level_view = false)
 {
     AliMat mat;
@@ -132,7 +132,7 @@ ALI_DEV double ali_band_eval(const AliModel &m, const AliModel *m_dev, const Ali
     if (level_view) ali_fetch_mat(m, g.mv, iz, ix, mat);
     else ali_fetch_mat_refined(m, g.mv.scale0, g.mv.side0, g.mv.mul0, g.mv.cast, iz, ix, mat);
     ali_band_gather(g, iz, ix, w);
-    double v = ali_update_window(m, mat, w, iz, ix, g.nz, g.nx, g.dnx, nullptr, sincos_tab);
+    double v = ali_update_window(m, mat, w, iz, ix, g.nz, g.nx, g.dnx, nullptr, mt);
     if (v == -1.0) {
         v = ali_band_fouds_slow(m_dev, g_mem, iz, ix);
         *fallback = 1;

@@ -213,7 +213,7 @@ __device__ __forceinline__ int ali_sort_bin(unsigned e, int isz, int isx)
 #define ALI_DMAP_BITS 9
 #define ALI_DMAP_WORDS ((1 << (2 * ALI_DMAP_BITS)) / 32)
 #define ALI_MARCH_SMEM_DMAP (ALI_DMAP_WORDS * 4)
-#define ALI_MARCH_SMEM_FIXED (ALI_MARCH_SMEM_DMAP + 404 * 4 * 8)
+#define ALI_MARCH_SMEM_FIXED (ALI_MARCH_SMEM_DMAP + ALI_MT_WORDS * 8)
 __device__ __forceinline__ void ali_dmap_row(unsigned *dmap, int z, int x0, unsigned pattern)
 {
     const unsigned m = (1u << ALI_DMAP_BITS) - 1u;
@@ -246,10 +246,10 @@ __device__ __forceinline__ bool ali_dmap_test(const unsigned *dmap, int iz, int 
 template <int NT>
 __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
 {
-    // dynamic shared memory: window-change bitmap | sin/cos table (csrc/ali_crmath.cuh) | optional band lists
+    // dynamic shared memory: window-change bitmap | sin/cos + atan tables (ali_glibcmath.cuh) | optional band lists
     extern __shared__ __align__(16) unsigned char s_raw[];
     unsigned *s_dmap = reinterpret_cast<unsigned *>(s_raw);
-    double *s_sincos = reinterpret_cast<double *>(s_raw + ALI_MARCH_SMEM_DMAP);
+    uint64_t *s_sincos = reinterpret_cast<uint64_t *>(s_raw + ALI_MARCH_SMEM_DMAP);
     unsigned char *s_lists = s_raw + ALI_MARCH_SMEM_FIXED;
     const int src = blockIdx.x;
     const int tid = threadIdx.x;
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
         wrk0 = ent1 + cap; wrk1 = wrk0 + cap;
     }
 
-    for (int q = tid; q < 404 * 4; q += NT) s_sincos[q] = ali_cr_sincos_tab[q];
+    for (int q = tid; q < ALI_MT_WORDS; q += NT) s_sincos[q] = q < ALI_GL_SINCOSTAB_COUNT ? ali_gl_sincostab[q] : ali_gl_atan_cij[q - ALI_GL_SINCOSTAB_COUNT];
     if (tid == 0) {
         s_grid = g;
         s_count[0] = 0; s_count[1] = 0; s_nwork[0] = 0; s_nwork[1] = 0;
@@ -597,7 +597,7 @@ template <int NT>
 __global__ void __launch_bounds__(NT) ali_march_cluster_kernel(AliBatch b, AliClusterCtl *ctl_all)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
-    double *s_sincos = reinterpret_cast<double *>(s_raw);
+    uint64_t *s_sincos = reinterpret_cast<uint64_t *>(s_raw);
     const int C = (int)ali_cluster_size(), rank = (int)ali_cluster_rank();
     const int src = blockIdx.x / C;
     const int tid = threadIdx.x, gtid = rank * NT + tid, GT = C * NT;
@@ -623,7 +623,7 @@ __global__ void __launch_bounds__(NT) ali_march_cluster_kernel(AliBatch b, AliCl
     double *val0 = b.stage + (size_t)src * 2 * cap, *val1 = val0 + cap;
     unsigned *ent0 = b.lists + (size_t)src * 4 * cap, *ent1 = ent0 + cap, *wrk0 = ent1 + cap, *wrk1 = wrk0 + cap;
 
-    for (int q = tid; q < 404 * 4; q += NT) s_sincos[q] = ali_cr_sincos_tab[q];
+    for (int q = tid; q < ALI_MT_WORDS; q += NT) s_sincos[q] = q < ALI_GL_SINCOSTAB_COUNT ? ali_gl_sincostab[q] : ali_gl_atan_cij[q - ALI_GL_SINCOSTAB_COUNT];
     if (tid == 0) {
         s_grid = g;
         s_evals = 0; s_fbs = 0;
@@ -1586,7 +1586,7 @@ static int ttf_attempt(alifmm_ctx *c, int32_t n_src, const int32_t *src_iz, cons
     // CTAs per source: a cluster when the batch leaves SMs idle (sources sharded over several GPUs)
     int csize = 1, cthreads = c->cluster_threads ? c->cluster_threads : 512;
     {
-        const size_t csmem = (size_t)404 * 4 * 8;
+        const size_t csmem = (size_t)ALI_MT_WORDS * 8;
         for (int cand : {8, 4, 2}) {
             if (c->cluster_size != 0 && c->cluster_size != cand) continue;
             cudaLaunchConfig_t cfg = {};
@@ -1612,7 +1612,7 @@ static int ttf_attempt(alifmm_ctx *c, int32_t n_src, const int32_t *src_iz, cons
         CUDA_TRY(cudaMemsetAsync(c->ctl.p, 0, (size_t)n_src * sizeof(AliClusterCtl), s));
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)(n_src * csize)); cfg.blockDim = dim3((unsigned)cthreads);
-        cfg.dynamicSmemBytes = (size_t)404 * 4 * 8; cfg.stream = s;
+        cfg.dynamicSmemBytes = (size_t)ALI_MT_WORDS * 8; cfg.stream = s;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = (unsigned)csize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;

@@ -29,18 +29,34 @@ double ali_emu_noise(double v)
 }
 extern "C" void emu_set_noise(double p, unsigned long long seed) { g_noise_p = p; if (seed) g_noise_state = seed; }
 
-// Which sin / cos / tan / atan the replay uses: 0 = glibc (what the reference runs on), 1 = the
-// device's accurate versions (csrc/ali_crmath.cuh; then the replay and the kernels produce the same bits).
+// Which sin / cos / tan / atan the replay uses: 0 = the running libm (what the reference runs on), 1 = the
+// device's functions (csrc/ali_glibcmath.cuh, the restatement of glibc's routines the kernels run).  The two
+// return the same bits; the switch exists to prove it (tests/test_kernel_replay.py).
 static int g_crmath = 0;
 extern "C" void emu_set_crmath(int on) { g_crmath = on; }
 extern "C" double emu_crmath_eval(int fn, double x)   // 0 atan, 1 sin, 2 cos, 3 tan
 {
-    return fn == 0 ? ali_cr_atan(x) : fn == 1 ? ali_cr_sin(x) : fn == 2 ? ali_cr_cos(x) : ali_cr_tan(x);
+    return fn == 0 ? ali_glibc_atan(x) : fn == 1 ? ali_glibc_sin(x) : fn == 2 ? ali_glibc_cos(x) : ali_glibc_tan(x);
 }
-double ali_emu_atan(double x) { return ali_emu_noise(g_crmath ? ali_cr_atan(x) : atan(x)); }
-double ali_emu_sin(double x) { return ali_emu_noise(g_crmath ? ali_cr_sin(x) : sin(x)); }
-double ali_emu_cos(double x) { return ali_emu_noise(g_crmath ? ali_cr_cos(x) : cos(x)); }
-double ali_emu_tan(double x) { return ali_emu_noise(g_crmath ? ali_cr_tan(x) : tan(x)); }
+// Bulk comparison of the device's functions with the running libm: n arguments, returns the number of results
+// whose bits differ (NaN == NaN), and the first offending argument.
+extern "C" long long emu_math_mismatches(int fn, const double *x, long long n, double *first_bad)
+{
+    long long bad = 0;
+    for (long long i = 0; i < n; i++) {
+        const double a = fn == 0 ? ali_glibc_atan(x[i]) : fn == 1 ? ali_glibc_sin(x[i]) : fn == 2 ? ali_glibc_cos(x[i]) : ali_glibc_tan(x[i]);
+        const double b = fn == 0 ? atan(x[i]) : fn == 1 ? sin(x[i]) : fn == 2 ? cos(x[i]) : tan(x[i]);
+        if (std::memcmp(&a, &b, 8) != 0 && !(a != a && b != b)) {
+            if (bad == 0 && first_bad) *first_bad = x[i];
+            bad++;
+        }
+    }
+    return bad;
+}
+double ali_emu_atan(double x) { return ali_emu_noise(g_crmath ? ali_glibc_atan(x) : atan(x)); }
+double ali_emu_sin(double x) { return ali_emu_noise(g_crmath ? ali_glibc_sin(x) : sin(x)); }
+double ali_emu_cos(double x) { return ali_emu_noise(g_crmath ? ali_glibc_cos(x) : cos(x)); }
+double ali_emu_tan(double x) { return ali_emu_noise(g_crmath ? ali_glibc_tan(x) : tan(x)); }
 
 struct HostModel {
     std::vector<AliMatRec> rec;

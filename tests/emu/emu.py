@@ -42,9 +42,20 @@ def set_coop(nlanes):
 
 
 def set_crmath(on):
-    """sin / cos / tan / atan of the replay: False = glibc (the reference's libm, default), True = the device's
-    accurate versions (csrc/ali_crmath.cuh) -- the replay then reproduces the kernels bit for bit."""
+    """sin / cos / tan / atan of the replay: False = the running libm (the reference's, default), True = the
+    device's functions (csrc/ali_glibcmath.cuh, glibc's own routines restated) -- same bits either way."""
     lib().emu_set_crmath(int(bool(on)))
+
+
+def math_mismatches(fn, x):
+    """Number of arguments in ``x`` for which the device's function (0 atan, 1 sin, 2 cos, 3 tan) and the
+    running libm return different bits, and the first such argument."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    first = ctypes.c_double(0.0)
+    f = lib().emu_math_mismatches
+    f.restype = ctypes.c_longlong
+    f.argtypes = [ctypes.c_int, _f64p, ctypes.c_longlong, ctypes.POINTER(ctypes.c_double)]
+    return int(f(int(fn), _p(x, _f64p), x.size, ctypes.byref(first))), first.value
 
 
 def set_tiled(on):
