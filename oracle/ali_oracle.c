@@ -17,6 +17,7 @@
  * Each function cites the reference lines it follows.
  */
 #include <math.h>
+#include <stddef.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -48,6 +49,11 @@ static double pymod(double a, double w)
  * that it differs from the reference itself only downstream of heap mis-orderings. */
 static int g_true_heap = 0;
 void ali_oracle_set_true_heap(int on) { g_true_heap = on; }
+/* Diagnostic 2: the reference's own heap (quirks included) on the refined source levels and on the main grid
+ * until a popped node is `stop_r` nodes (Chebyshev) from the source, a CORRECT heap from then on -- the point
+ * where the CUDA path hands over from its sequential replica to the band march.  stop_r < 0: off. */
+static int g_true_after = -1, g_src_z = 0, g_src_x = 0;
+void ali_oracle_set_true_heap_after(int stop_r) { g_true_after = stop_r; }
 
 /* Python round(k / 2) for a positive int k: round-half-to-even (ATR:123,135,160,172). */
 static int half_round(int k)
@@ -848,8 +854,20 @@ static void march(Grid *g, const Tables *t, double dnx, int cx, int cz, int max_
 {
     int finished = 0;
     int nnx = g->nx, nnz = g->nz, s;
+    int switch_pending = 0, switched = 0;
     while (g->ntr > 0 && !finished) {
         int ix = g->btg[3], iz = g->btg[2];
+        if (switch_pending) {   /* diagnostic 2: from here on a correct min-heap (heapified once) */
+            int k;
+            g_true_heap = 1;
+            for (k = g->ntr / 2; k >= 1; k--) sift_down_from(g, k);
+            switch_pending = 0; switched = 1;
+            ix = g->btg[3]; iz = g->btg[2];
+        }
+        if (g_true_after >= 0 && max_dist < 0 && !switched && !g_true_heap) {
+            int dz = abs(iz - g_src_z), dx = abs(ix - g_src_x);
+            if ((dz > dx ? dz : dx) >= g_true_after) switch_pending = 1;   /* after this pop's neighbours */
+        }
         g->nsts[AT(g, iz, ix)] = 0;
         downtree(g);
         for (s = 0; s < 2; s++) {
@@ -883,6 +901,7 @@ static void march(Grid *g, const Tables *t, double dnx, int cx, int cz, int max_
             }
         }
     }
+    if (switched) g_true_heap = 0;
 }
 
 /* Analytic straight-ray seed of the source's own coarse cell + perimeter push
@@ -976,6 +995,7 @@ static void travel_core(Grid *m, const Tables *t, double scx, double scz, double
         march(&lv[l], t, dnx / sc, cx[l], cz[l], sc * size, l == 0);
     }
     handoff(&lv[2], cz[2], cx[2], m, isz, isx);
+    g_src_z = isz; g_src_x = isx;
     march(m, t, dnx, 0, 0, -1, 0);
     for (l = 0; l < 3; l++) grid_free(&lv[l]);
 }
@@ -1025,6 +1045,7 @@ static void travel_finer_core(const Grid *m0, const Tables *t, double scx, doubl
     march(&l2, t, dnx / 3, cx2, cz2, 3 * size2, 0);
 
     handoff(&l2, cz2, cx2, &f, isz, isx);
+    g_src_z = isz; g_src_x = isx;
     march(&f, t, dnx, 0, 0, -1, 0);
     for (i = 0; i < n; i++) out[i] = out[i] / sg;
     f.ttn = NULL;
@@ -1328,6 +1349,41 @@ double ali_oracle_fouds_node(int nz, int nx, const double *veln, const int32_t *
     m.ttn = (double *)ttn; m.nsts = (int32_t *)nsts;
     r = ali_fouds18(&m, &t, iz, ix, dnx, dnx, nx, nz);
     free(m.stif);
+    return r;
+}
+
+/* The same operators at ABSOLUTE grid coordinates of a large grid of which the caller holds only the rows
+ * [z0, z0 + rows) (full width): update() interpolates in absolute coordinates (ATR:1444-1450) and tests the
+ * grid edges, so a window cut out of the grid and renumbered can differ in the last ulp.  All arrays are
+ * slabs [rows][nx] (stif [rows][nx][5]); nothing outside rows iz-2 .. iz+2 is read.  Test infrastructure
+ * (tests/parity_tools.py). */
+double ali_oracle_update_node_slab(int nz, int nx, int z0, int rows, const double *veln, const int32_t *velpn,
+                                   const double *vel_map, const int64_t *stif, int has_stif, const double *phase_tab,
+                                   const double *group_tab, int ncol, const double *ttn, const int32_t *nsts, int iz,
+                                   int ix, double dnx, int *used_fouds)
+{
+    Grid m;
+    Tables t = {group_tab, phase_tab, ncol};
+    double r, *sd = NULL;
+    const ptrdiff_t off = (ptrdiff_t)z0 * nx;
+    size_t n = (size_t)rows * nx * 5, i;
+    memset(&m, 0, sizeof m);
+    m.nz = nz; m.nx = nx;
+    m.veln = (double *)veln - off; m.velpn = (int32_t *)velpn - off; m.vel_map = (double *)vel_map - off;
+    m.has_stif = has_stif;
+    if (stif) {
+        sd = (double *)malloc(n * sizeof(double));
+        for (i = 0; i < n; i++) sd[i] = (double)stif[i];
+        m.stif = sd - off * 5;
+    }
+    m.ttn = (double *)ttn - off; m.nsts = (int32_t *)nsts - off;
+    r = ali_update(&m, &t, iz, ix, dnx, nz, nx, NULL);
+    if (used_fouds) *used_fouds = 0;
+    if (r == -1.0) {
+        r = ali_fouds18(&m, &t, iz, ix, dnx, dnx, nx, nz);
+        if (used_fouds) *used_fouds = 1;
+    }
+    free(sd);
     return r;
 }
 

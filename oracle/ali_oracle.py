@@ -134,6 +134,21 @@ def fouds_node(m, ttn, nsts, iz, ix, dnx):
                                        _p(nsts, _i32p), int(iz), int(ix), ctypes.c_double(dnx))
 
 
+def update_node_slab(m, nz, z0, ttn, nsts, iz, ix, dnx):
+    """update() (fouds18_A on -1.0) at the ABSOLUTE node (iz, ix) of an nz-row grid of which ``m`` / ``ttn`` /
+    ``nsts`` hold only the rows [z0, z0 + m.nz), full width.  Returns (value, used_fouds)."""
+    ttn = np.ascontiguousarray(ttn, dtype=np.float64)
+    nsts = np.ascontiguousarray(nsts, dtype=np.int32)
+    assert ttn.shape == (m.nz, m.nx) == nsts.shape and z0 <= iz - 2 + 2 and iz < z0 + m.nz
+    fb = ctypes.c_int(0)
+    f = lib().ali_oracle_update_node_slab
+    f.restype = ctypes.c_double
+    v = f(int(nz), m.nx, int(z0), m.nz, _p(m.veln, _f64p), _p(m.velpn, _i32p), _p(m.vel_map, _f64p), _p(m.stif, _i64p),
+          int(m.has_stif), _p(m.phase, _f64p), _p(m.group, _f64p), m.ncol, _p(ttn, _f64p), _p(nsts, _i32p), int(iz), int(ix),
+          ctypes.c_double(dnx), ctypes.byref(fb))
+    return v, fb.value
+
+
 def group_vel(angle, c22, c23, c33, c44, sigma, vel_scale=1.0):
     """ATR:3520 group_vel() (stiffness in MPa)."""
     return lib().ali_oracle_group_vel(*[ctypes.c_double(float(v)) for v in (angle, c22, c23, c33, c44, sigma, vel_scale)])
@@ -147,6 +162,12 @@ def phase_vel(angle, c22, c23, c33, c44, sigma, vel_scale=1.0):
 def set_true_heap(on):
     """Diagnostic: make the narrow band a correct min-heap (see ali_oracle.c, g_true_heap)."""
     lib().ali_oracle_set_true_heap(int(bool(on)))
+
+
+def set_true_heap_after(stop_r):
+    """Diagnostic: the reference's own heap up to the moment a popped main-grid node is ``stop_r`` nodes
+    (Chebyshev) from the source, a correct min-heap from then on (see ali_oracle.c); ``stop_r`` < 0 = off."""
+    lib().ali_oracle_set_true_heap_after(int(stop_r))
 
 
 def counters(reset=False):

@@ -69,6 +69,32 @@ def _check_field(ref, got, frac=0.999, worst=2e-3, med=1e-9, what=""):
     return e
 
 
+def _explained(orc, m, ref, T, sg, src, what=""):
+    """Where the CUDA field differs from the reference's, why?  The device runs the reference's operator on
+    the reference's libm bits, so only the ORDER in which nodes see each other can differ -- and the reference's
+    order is that of a heap that mis-orders (parent index round(k/2) with banker's rounding, ATR:123; updates
+    only sift up although they may raise a value, ATR:141-175).  The oracle can run the reference's algorithm
+    with that heap ordering correctly from the hand-over radius on (ali_oracle.set_true_heap_after: the refined
+    source levels and the main grid up to the hand-over keep the reference's own heap, which the sequential
+    replica reproduces).  The CUDA field must equal THAT field: bit for bit, or -- where the reference's lazy
+    re-evaluation trigger (only when a 4-neighbour pops, ATR:2065-2102) leaves a stale last digit -- within 1e-12.
+    So every deviation from the shipped reference beyond 1e-12 is the reference's heap mis-ordering."""
+    stop_r = (13 if sg == 1 else 5 * sg + (sg - 1) // 2) + 27      # last refined box + handover_margin (alifmm_set_option)
+    om = _omodel(orc, m)
+    orc.set_true_heap_after(stop_r)
+    try:
+        fixed = orc.travel(om, m["dnx"] * src[1], m["dnx"] * src[0], m["dnx"]) if sg == 1 else \
+            orc.travel_finer_grid(om, m["dnx"] * src[1], m["dnx"] * src[0], m["dnx"], sg)
+    finally:
+        orc.set_true_heap_after(-1)
+    e = models.rel_err(fixed, T)
+    d = models.rel_err(ref, T)
+    print("%s: differs from the reference on %.4f of the nodes (%.5f beyond 1e-5, max %.1e); from the reference on a "
+          "correct heap on %.6f (max %.1e)" % (what, (ref != T).mean(), (d > TOL_NODE).mean(), d.max(), (fixed != T).mean(), e.max()))
+    assert e.max() <= 1e-12, (what, e.max(), (fixed != T).mean())
+    return {"bit_equal_fixed": float((fixed == T).mean()), "max_fixed": float(e.max()), "deviating": float((ref != T).mean())}
+
+
 def _nodes(m, scx, scz):
     return (np.round(np.asarray(scz) / m["dnx"]).astype(np.int32), np.round(np.asarray(scx) / m["dnx"]).astype(np.int32))
 
@@ -87,20 +113,34 @@ def test_notebook_fields_match_oracle_and_golden(capi, orc, name):
     # as in the reference -- also on the homogeneous, axis-aligned tabulated medium, where a last-ulp change of
     # atan moves 40 % of the nodes (tests/test_kernel_replay.py::test_replay_last_ulp_sensitivity_of_symmetric_media;
     # round 1's correctly rounded functions left 6 % of the second field beyond 1e-5).
+    # Measured on B200 (gpurun_out/parity_survey.json, PARITY.md): 5 of the 7 fields equal the reference's bit for
+    # bit; the Christoffel field of source 1 differs by <= 2.5e-14 on 4 % of its nodes and the tabulated field of
+    # source 1 by up to 2.9e-2 on 5.9 % -- both behind ONE node each where the reference's heap popped late
+    # (_explained).  The tabulated medium is homogeneous and axis-aligned: stencils tie everywhere and a single
+    # different choice moves everything downstream (test_replay_last_ulp_sensitivity_of_symmetric_media).
+    exact = {"gradient": (0, 1), "christoffel": (0, 2), "table": (0,)}[name]
     for k in range(len(iz)):
         ref = orc.travel(om, m["scx"][k], m["scz"][k], m["dnx"])
         e = models.rel_err(ref, T[k])
         print("%s field %d: max rel err %.3e, bit-equal nodes %.6f" % (name, k, e.max(), (ref == T[k]).mean()))
-        assert e.max() <= TOL_BITS, (name, k, e.max())
+        if k in exact:
+            assert np.array_equal(ref, T[k]), (name, k, e.max())
+        else:
+            _explained(orc, m, ref, T[k], 1, (iz[k], ix[k]), what="%s field %d" % (name, k))
+            if name == "christoffel":
+                assert e.max() <= 1e-13
+            else:
+                assert (e > TOL_NODE).mean() <= 0.12 and e.max() <= 6e-2   # (2 x measured)
         assert T[k][iz[k], ix[k]] == 0.0
     gold = _load("golden_fields.npz")
     if name == "gradient":   # straight from the reference (notebook cell 12)
-        assert models.rel_err(gold["nb1_T0"], T[0]).max() <= TOL_BITS
+        assert np.array_equal(gold["nb1_T0"], T[0])
         assert abs(T[0].sum() - 1.3402942867072842) <= 1e-12
     elif name == "christoffel":
-        assert models.rel_err(gold["nb3_sub"], T[:, ::4, ::4]).max() <= TOL_BITS
+        assert models.rel_err(gold["nb3_sub"], T[:, ::4, ::4]).max() <= 1e-13
+        assert np.array_equal(gold["nb3_sub"][0], T[0, ::4, ::4]) and np.array_equal(gold["nb3_T2"], T[2])
     else:
-        assert models.rel_err(gold["nb2_sub"], T[:, ::4, ::4]).max() <= TOL_BITS
+        assert np.array_equal(gold["nb2_sub"][0], T[0, ::4, ::4])
     ctx.close()
 
 
@@ -112,8 +152,12 @@ def test_weld_coarse_fields_match_reference_golden(capi, orc):
     src = gold["weld1_src"]
     T = ctx.ttf(src[:, 1].astype(np.int32), src[:, 0].astype(np.int32), 1)
     for k in range(len(src)):
-        _check_field(gold["weld1_sub"][k], T[k][::4, ::4], worst=1e-4, med=1e-7, what=k)
-        assert abs(T[k].sum() - gold["weld1_sum"][k]) <= 1e-7 * gold["weld1_sum"][k]
+        # measured: sources 0, 1, 3 bit-identical to the reference; source 2 (interior, z=200, x=250) within 8e-13
+        # (6 % of its nodes, behind one reference heap glitch: test_deviations_are_downstream_of_reference_heap_glitches)
+        e = models.rel_err(gold["weld1_sub"][k], T[k][::4, ::4])
+        print("weld coarse source %d: max rel err %.2e" % (k, e.max()))
+        assert e.max() <= 2e-12, (k, e.max())
+        assert abs(T[k].sum() - gold["weld1_sum"][k]) <= 1e-12 * gold["weld1_sum"][k]
     c = ctx.counters()
     assert c["node_solves"] == 4 * 424 * 500 and c["band_rounds_max"] > 100 and c["kernel_launches"] == 3
     ctx.close()
@@ -183,15 +227,12 @@ def test_voronoi_config4_fields_match_oracle(capi, orc):
         ref = orc.travel(om, scx[k], scz[k], m["dnx"])
         # 0-2 % of the nodes (depending on the source; measured 0.9800 ... 1.0000 within 1e-5) sit behind a heap glitch of the reference (DESIGN.md 3,
         # tests/test_kernel_replay.py::test_replay_deviations_start_at_reference_glitches) ...
-        _check_field(ref, T[k], frac=0.97, med=1e-7, worst=5e-3, what=("voronoi", k))
+        _check_field(ref, T[k], frac=0.97, med=1e-12, worst=5e-3, what=("voronoi", k))
+        _explained(orc, m, ref, T[k], 1, (iz[k], ix[k]), what="voronoi 768 source %d" % k)
         if k in (0, 5):
-            # ... and the kernel agrees with the host replay of its algorithm to rounding level, except
-            # behind the rare node where one ulp of atan/sin/cos decides between two stencils (source 5:
-            # 0.9 % of the nodes; the replay with injected ulp noise shows the same effect,
-            # tests/test_kernel_replay.py::test_replay_last_ulp_sensitivity*)
+            # ... and the kernel equals the host replay of its algorithm (on the running libm) bit for bit
             R, _, rc = emu.ttf(om, m["dnx"], int(iz[k]), int(ix[k]), 1)
-            d = models.rel_err(R, T[k])
-            assert rc == 0 and (d <= 1e-5).mean() >= 0.98 and np.median(d) <= 1e-12 and d.max() <= 5e-3
+            assert rc == 0 and np.array_equal(R, T[k]), models.rel_err(R, T[k]).max()
     ctx.close()
 
 
@@ -211,7 +252,8 @@ def test_voronoi_config4_full_size(capi, orc):
     assert c["node_solves"] == 4 * n * n
     om = _omodel(orc, m)
     ref = orc.travel(om, scx[sel[1]], scz[sel[1]], m["dnx"])
-    _check_field(ref, T[1], frac=0.99, med=1e-10, worst=5e-3, what="voronoi 4096")
+    _check_field(ref, T[1], frac=0.99, med=1e-12, worst=5e-3, what="voronoi 4096")
+    _explained(orc, m, ref, T[1], 1, (iz[1], ix[1]), what="voronoi 4096")
     alone = ctx.ttf(iz[2:3], ix[2:3], 1)[0]
     assert np.array_equal(alone, T[2])
     rng = np.random.default_rng(5)
@@ -250,11 +292,12 @@ def test_long_grid_config5_proxy(capi, orc):
     # a long channel carries every reference heap glitch to its end: 26 % of the nodes end up
     # 1.1e-5 ... 2e-5 from the reference, none beyond 2.4e-3 (see the replay test named above) ...
     assert (e <= 2e-5).mean() >= 0.9 and (e <= 1e-4).mean() >= 0.9999 and e.max() <= 5e-3 and np.median(e) <= 1e-8
-    # ... while the kernel and the host replay of its algorithm agree to rounding level
+    # ... while the kernel and the host replay of its algorithm (on the running libm) give the same bits, and all of
+    # it starts at reference heap glitches
     from tests.emu import emu
     R, _, rc = emu.ttf(om, m["dnx"], 8192, 96, 1)
-    d = models.rel_err(R, T)                # (last-ulp libm differences can flip a stencil at isolated nodes)
-    assert rc == 0 and (d <= 1e-5).mean() >= 0.98 and np.median(d) <= 1e-12 and d.max() <= 5e-3
+    assert rc == 0 and np.array_equal(R, T), models.rel_err(R, T).max()
+    _explained(orc, m, ref, T, 1, (8192, 96), what="16384 x 192 strip")
     ctx.close()
 
 
@@ -325,11 +368,11 @@ def test_weld_sg9_headline_field_against_reference(capi):
     ctx = _ctx(capi, w)
     T = ctx.ttf(np.array([423], dtype=np.int32), np.array([160], dtype=np.int32), 9)[0]
     assert T.shape == (3808, 4492)
-    e = models.rel_err(gold["weld9_sub"], T[::16, ::16])
-    assert (e <= TOL_NODE).mean() >= 0.97, ((e <= TOL_NODE).mean(), e.max())
-    assert np.median(e) <= 2e-6 and e.max() <= 5e-3
-    assert abs(T.sum() - gold["weld9_stats"][0]) <= 1e-5 * gold["weld9_stats"][0]
-    assert abs(T.max() - gold["weld9_stats"][1]) <= 1e-4 * gold["weld9_stats"][1]
+    # measured on B200: all 17,105,536 nodes equal the oracle's bit for bit (PARITY.md); against the reference's
+    # own sub-sampled output and checksums (round 1's correctly rounded device math left 0.44 % beyond 1e-5):
+    assert np.array_equal(gold["weld9_sub"], T[::16, ::16]), models.rel_err(gold["weld9_sub"], T[::16, ::16]).max()
+    assert abs(T.sum() - gold["weld9_stats"][0]) <= 1e-13 * gold["weld9_stats"][0]
+    assert T.max() == gold["weld9_stats"][1]
     c = ctx.counters()
     assert c["node_solves"] == 3808 * 4492
     ctx.close()
@@ -510,13 +553,13 @@ def test_weld_sg9_rays_against_reference(capi):
     pairs[:4, 4] = 1
     fm = ALI_FMM(w["veln"], w["velpn"], w["vel_map"], scx, scz, stif_den=w["stif_den"], dnx=w["dnx"])
     times = fm.find_all_TTF_rays(w["veln"], w["velpn"], w["vel_map"], trans_pairs=pairs, stif_den=w["stif_den"])
-    good = 0
+    # the field of receiver 40 equals the reference's bit for bit (test_weld_sg9_headline_field_against_reference),
+    # so its rays do too: every point, every time
     for k in range(4):
         x, y = fm.ray_path(k, 4)
-        dev = models.polyline_distance(x, y, gold["weld9_ray_x_%d" % k], gold["weld9_ray_y_%d" % k])
-        assert abs(times[k, 4] - gold["weld9_ray_times"][k]) <= 1e-4 * gold["weld9_ray_times"][k]
-        good += dev <= TOL_CELL
-    assert good >= 3
+        gx, gy = gold["weld9_ray_x_%d" % k], gold["weld9_ray_y_%d" % k]
+        assert len(x) == len(gx) and np.abs(x - gx).max() <= 1e-9 and np.abs(y - gy).max() <= 1e-9, k
+        assert abs(times[k, 4] - gold["weld9_ray_times"][k]) <= 1e-12 * gold["weld9_ray_times"][k]
 
 
 def test_weld_rays_py_script_workflow(capi, tmp_path):
@@ -545,15 +588,32 @@ def test_weld_rays_py_script_workflow(capi, tmp_path):
             assert (rx[i, j, 0], ry[i, j, 0]) == (fm.isx[i], fm.isz[i]) and (rx[i, j, n - 1], ry[i, j, n - 1]) == (fm.isx[j], fm.isz[j])
             assert rx[i, j, :n].min() >= 0 and rx[i, j, :n].max() <= 499 and ry[i, j, :n].min() >= 0 and ry[i, j, :n].max() <= 423
             assert not rx[i, j, n:].any()
-    # the rays the reference itself produced for receiver 40 (tests/golden/make_golden.py)
-    gold = _load("golden_rays.npz")
-    good = 0
-    for k, sx in enumerate(gold["weld9_ray_srcx"]):
-        i = int(round((sx - 25) / 15))
-        x, y = fm.ray_path(i, 40)
-        assert abs(trav_times[i, 40] - gold["weld9_ray_times"][k]) <= 1e-4 * gold["weld9_ray_times"][k]
-        good += models.polyline_distance(x, y, gold["weld9_ray_x_%d" % k], gold["weld9_ray_y_%d" % k]) <= TOL_CELL
-    assert good >= 3
+    # The whole run against the REAL reference's output of the same script (tests/golden/golden_weld_rays.npz,
+    # make_golden_weld_rays.py; BASELINE.md section 2 quotes its scalars).  Measured on B200: ray_len.sum() equal,
+    # times.sum() to 1e-7, 944 of the 961 paths within 0.1 cell (935 within 0.01) -- the other 17 run through
+    # one of the fields that differ from the reference behind a reference heap glitch (PARITY.md) and settle on
+    # a neighbouring branch of nearly equal time (worst 4.2 cells, 5e-4 in time).
+    g = _load("golden_weld_rays.npz")
+    assert abs(g["times"].sum() - 0.01527291403909612) <= 1e-15 and g["ray_len"].sum() == 524461
+    assert abs(trav_times.sum() - g["times"].sum()) <= 1e-5 * g["times"].sum()
+    assert abs(int(fm.ray_len.sum()) - 524461) <= 524      # within 0.1 %
+    for i, j, v in ((0, 31, 1.461554973641925e-05), (30, 31, 2.0367740326699965e-05), (15, 46, 1.5397920119148576e-05)):
+        assert abs(trav_times[i, j] - v) <= 1e-4 * v, (i, j, trav_times[i, j])
+    assert int(fm.ray_len[fm.ray_len > 0].min()) == 424 and abs(int(fm.ray_len.max()) - 873) <= 2
+    rel = np.abs(trav_times - g["times"])[g["times"] > 0] / g["times"][g["times"] > 0]
+    assert rel.max() <= 1e-3 and np.median(rel) <= 1e-12, (rel.max(), np.median(rel))
+    near = exact = 0
+    for k in range(len(g["pair_i"])):
+        i, j = int(g["pair_i"][k]), int(g["pair_j"][k])
+        gx = g["path_x"][g["offsets"][k]:g["offsets"][k + 1]].astype(np.float64)
+        gy = g["path_y"][g["offsets"][k]:g["offsets"][k + 1]].astype(np.float64)
+        x, y = fm.ray_path(i, j)
+        d = models.polyline_distance(x, y, gx, gy)
+        near += d <= TOL_CELL
+        exact += d <= 1e-3     # (the fixture stores float32 coordinates)
+    print("Weld_rays.py run: %d of 961 paths within 0.1 cell of the reference's, %d within 0.001; times.sum() rel %.2e, worst time rel %.2e" % (
+        near, exact, abs(trav_times.sum() - g["times"].sum()) / g["times"].sum(), rel.max()))
+    assert near >= 927 and exact >= 900      # (measured 944 / 935; twice the misses allowed)
 
 
 # ----------------------------------------------------------------------------- reference-facing API
@@ -626,12 +686,41 @@ def test_material_curves_and_model_scan_on_device(capi, orc):
     ctx.close()
 
 
+def test_cuda_equals_the_reference_algorithm_on_a_correct_heap(capi, orc):
+    """The parity statement of this repo (PARITY.md): the CUDA path computes, bit for bit, what the reference's
+    own algorithm computes when its narrow-band heap orders correctly beyond the hand-over radius (_explained).
+    Models on which the shipped reference deviates -- the notebook's tabulated medium (5.9 % of the nodes beyond
+    1e-5), a 16384-long strip (26 %), Voronoi grains, the weld at subgrid 1 and 9 (a headline-size field with 40 %
+    of its nodes different from the shipped reference, 3.8 % beyond 1e-5)."""
+    from Anis_TTF_rays import ALI_FMM
+    import tests.test_kernel_replay as tk
+    vor = models.voronoi(768, 144, 1234)
+    cases = [("notebook table medium, source 1", models.notebook_table(ALI_FMM), (140, 199), 1),
+             ("notebook Christoffel medium, source 1", models.notebook_christoffel(), (140, 199), 1),
+             ("notebook gradient medium, subgrid 9", models.notebook_gradient(), (30, 1), 9),
+             ("weld coarse, interior source", models.weld(), (200, 250), 1),
+             ("voronoi 768", vor, (480, 288), 1), ("voronoi 768", vor, (480, 480), 1), ("voronoi 768", vor, (96, 96), 1),
+             ("2048 x 192 strip of 64 x 64 blocks", tk._strip_model(2048, 192, 11), (1024, 96), 1),
+             ("weld subgrid 9 (headline grid), transducer at x=300 bottom", models.weld(), (423, 300), 9)]
+    deviating = exact = 0
+    for what, m, (sz, sx), sg in cases:
+        ctx = _ctx(capi, m)
+        T = ctx.ttf(np.array([sz], dtype=np.int32), np.array([sx], dtype=np.int32), sg)[0]
+        ctx.close()
+        om = _omodel(orc, m)
+        ref = orc.travel(om, m["dnx"] * sx, m["dnx"] * sz, m["dnx"]) if sg == 1 else orc.travel_finer_grid(om, m["dnx"] * sx, m["dnx"] * sz, m["dnx"], sg)
+        r = _explained(orc, m, ref, T, sg, (sz, sx), what=what)
+        deviating += r["deviating"] > 0
+        exact += r["bit_equal_fixed"] == 1.0
+    assert deviating >= 7      # (the check is not vacuous: these fields do differ from the shipped reference)
+    assert exact >= 7          # (measured: all but the two stale-last-digit cases, <= 8e-13)
+
+
 # ----------------------------------------------------------------------------- node-level operators (rows a1-a3, f3)
 def test_node_level_update_and_fouds_on_device(capi):
     """Device update() (ATR:904-1410) and fouds18_A() (ATR:240-901) on the 4000 committed states the
     REAL reference evaluated (tests/golden/golden_ops.npz, make_golden.py): same no-solution (-1.0)
-    pattern, values equal to the reference's to a few ulps (the device's atan / sin / cos / tan differ
-    from glibc's in the last ulp in 0.1 % of the calls)."""
+    pattern, values equal to the reference's bit for bit."""
     ops = _load("golden_ops.npz")
     upd, fou, sten = capi.eval_nodes(ops["veln"], ops["velpn"], ops["vel_map"], ops["stif"], True, ops["group_tab"],
                                      ops["phase_tab"], float(ops["dnx"]), ops["ttn"], ops["nsts"], ops["pos"])
@@ -643,8 +732,8 @@ def test_node_level_update_and_fouds_on_device(capi):
     ulp = 2.0 ** -52
     print("update: max %.2e, >1ulp %d of %d; fouds: max %.2e, >1ulp %d" % (eu.max(), (eu > ulp).sum(), eu.size, ef.max(),
                                                                             (ef > ulp).sum()))
-    assert eu.max() <= 8 * ulp and (eu <= ulp).mean() >= 0.99
-    assert ef.max() <= 8 * ulp and (ef <= ulp).mean() >= 0.99
+    # measured on B200: every bit equal (the device's atan / sin / cos / tan are glibc's own routines)
+    assert eu.max() == 0.0 and ef.max() == 0.0
 
 
 def test_fouds_fallback_fires_where_the_oracle_fires(capi, orc):
@@ -670,7 +759,7 @@ def test_fouds_fallback_fires_where_the_oracle_fires(capi, orc):
         e = models.rel_err(ref, T)
         print("fallback: oracle %d, device %d, max rel err %.2e" % (n_fouds, c["fallback_evals"], e.max()))
         assert c["fallback_evals"] >= n_fouds
-        assert e.max() <= TOL_EXACT
+        assert e.max() == 0.0
 
 
 @pytest.mark.parametrize("shape,sg", [((1024, 40), 1), ((1024, 48), 1), ((160, 14), 3), ((40, 300), 1)])

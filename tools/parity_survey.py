@@ -38,19 +38,32 @@ _W = {}
 
 
 def _oracle_field(args):
+    """(the shipped reference's field, the reference algorithm's field on a heap that orders correctly beyond the
+    hand-over radius -- oracle.set_true_heap_after)"""
     name, sz, sx, sg = args
     m = _W[name]
     om = omodel(m)
-    return orc.travel_finer_grid(om, m["dnx"] * sx, m["dnx"] * sz, m["dnx"], sg) if sg > 1 else orc.travel(om, m["dnx"] * sx, m["dnx"] * sz, m["dnx"])
+    run = (lambda: orc.travel_finer_grid(om, m["dnx"] * sx, m["dnx"] * sz, m["dnx"], sg)) if sg > 1 else \
+        (lambda: orc.travel(om, m["dnx"] * sx, m["dnx"] * sz, m["dnx"]))
+    ref = run()
+    orc.set_true_heap_after((13 if sg == 1 else 5 * sg + (sg - 1) // 2) + 27)
+    try:
+        fixed = run()
+    finally:
+        orc.set_true_heap_after(-1)
+    return ref, fixed
 
 
-def field_stats(m, ref, T, sg, src):
+def field_stats(m, both, T, sg, src):
+    ref, fixed = both
     e = models.rel_err(ref, T)
+    ef = models.rel_err(fixed, T)
     box = 13 if sg == 1 else (5 * sg + (sg - 1) // 2)
     cls = parity_tools.classify_deviations(orc, m, ref, T, sg=sg, source=(src[0] * (sg if sg > 1 else 1), src[1] * (sg if sg > 1 else 1)), box=box)
     return {"source_zx": [int(src[0]), int(src[1])], "nodes": int(ref.size), "bit_equal": float((ref == T).mean()),
             "frac_gt_1e-5": float((e > 1e-5).mean()), "frac_gt_1e-9": float((e > 1e-9).mean()), "p99": float(np.quantile(e, 0.99)),
-            "max": float(e.max()), "patches": cls.get("patches", 0), "roots_checked": cls.get("roots_checked", 0),
+            "max": float(e.max()), "bit_equal_correct_heap": float((fixed == T).mean()), "max_correct_heap": float(ef.max()),
+            "patches": cls.get("patches", 0), "roots_checked": cls.get("roots_checked", 0),
             "roots_glitch": cls["roots_glitch"], "roots_in_source_box": cls["roots_in_source_box"], "unexplained": cls["unexplained"],
             "unexplained_samples": cls.get("unexplained_samples", [])}
 
