@@ -100,10 +100,18 @@ def voronoi(n, n_seeds, seed, dnx=1e-4):
     pts = rng.uniform(0, n, size=(n_seeds, 2))
     ori = rng.uniform(0, 180, size=n_seeds)
     from scipy.spatial import cKDTree
-    zz, xx = np.mgrid[0:n, 0:n]
-    _, idx = cKDTree(pts).query(np.stack([zz.ravel(), xx.ravel()], axis=1), workers=-1)
-    veln = ori[idx].reshape(n, n)
-    return dict(veln=veln, velpn=np.zeros((n, n), dtype=int), vel_map=np.ones((n, n)), stif_den=const_stif((n, n)),
+    tree = cKDTree(pts)
+    veln = np.empty((n, n))
+    rows = max(1, (1 << 24) // n)          # nearest seed of every node, a block of rows at a time (bounded memory)
+    xx = np.arange(n, dtype=np.float64)
+    for z0 in range(0, n, rows):
+        z1 = min(n, z0 + rows)
+        q = np.empty(((z1 - z0) * n, 2))
+        q[:, 0] = np.repeat(np.arange(z0, z1, dtype=np.float64), n)
+        q[:, 1] = np.tile(xx, z1 - z0)
+        _, idx = tree.query(q, workers=-1)
+        veln[z0:z1] = ori[idx].reshape(z1 - z0, n)
+    return dict(veln=veln, velpn=np.zeros((n, n), dtype=np.int32), vel_map=np.ones((n, n)), stif_den=const_stif((n, n)),
                 dnx=dnx)
 
 

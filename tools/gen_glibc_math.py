@@ -453,7 +453,7 @@ def main():
                  "// derived from %s, %s.\n"
                  "// Round-to-nearest only; arguments beyond glibc's medium range fall back to the platform's function.\n"
                  "#pragma once\n#include <stdint.h>\n#include <string.h>\n#include <math.h>\n\n"
-                 "#if defined(__CUDACC__)\n#define ALI_GL_DEV __device__ __forceinline__\n#define ALI_GL_INL __device__ __forceinline__\n"
+                 "#if defined(__CUDACC__)\n#if defined(ALI_GL_NOINLINE)\n#define ALI_GL_DEV __device__ __noinline__\n#else\n#define ALI_GL_DEV __device__ __forceinline__\n#endif\n#define ALI_GL_INL __device__ __forceinline__\n"
                  "#define ALI_GL_TABLE static __device__ const\n"
                  "#define ALI_GL_FMA(a, b, c) __fma_rn((a), (b), (c))\n"
                  "#define ALI_GL_D(u) __longlong_as_double((long long)(u))\n#define ALI_GL_B(d) ((uint64_t)__double_as_longlong(d))\n"
