@@ -440,7 +440,12 @@ ALI_DEV int ali_coop_advance(AliSeqGrid &g, AliCoopState &cs, int cx, int cz, in
             if (s == 0) x = ix - 1; else if (s == 1) x = ix + 1; else if (s == 2) z = iz - 1; else z = iz + 1;
             const bool inside = (s < 2) ? (0 <= x && x <= nnx - 1) : (0 <= z && z <= nnz - 1);
             if (inside) {
+                // A neighbour of a popped node is always inside the status window: level grids store every node,
+                // and on the main grid the march stops at the first pop stop_r nodes from the source while the
+                // window reaches stop_r + 4 (ali_src_main_geometry).  The host replay keeps the check.
+#if !defined(__CUDA_ARCH__)
                 if (!g.in_win(z, x)) { cs.finished = 1; cs.why = ALI_SEQ_LIMIT; continue; }
+#endif
                 const unsigned wi = cs.wi + (unsigned)(s == 0 ? -1 : s == 1 ? 1 : s == 2 ? -g.wnx : g.wnx);
                 // the neighbour's state in one go (independent loads; T is stored window-indexed like the rest:
                 // t[z * t_stride + x - toff] == t[wi] for every grid the march runs on)

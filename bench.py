@@ -444,7 +444,7 @@ def run_gpu(args):
             "l2_policy": "inputs_larger_than_l2 (%.2f GB of field state per rank and step)" % (my_nodes * 17 / 1e9),
             "ms_seq_kernel": seq_ms, "ms_march_kernel": march_ms, "ms_rays_kernel": rays_ms,
             "ms_finalize_kernel": statistics.mean(acc["ms_finalize"]) if acc["ms_finalize"] else 0.0,
-            "delta_frac": args.delta_frac or 0.3,
+            "delta_frac": args.delta_frac or 0.35,
         })
         if c1:
             line["config"].update({
@@ -466,7 +466,7 @@ def run_gpu(args):
             "kernel": "ali_march_cluster_kernel" if c1 and c1["cluster_size"] > 1 else "ali_march_kernel", "peak_source": peak_src,
             "algorithmic_bytes_per_launch": my_nodes * B_ALG,
             "frac_seq_plus_march": achieved_ttf / peak,
-            "note": "per rank (rank 0).  The march is round-latency bound (one barrier-separated round per 0.3 dnx/vmax of "
+            "note": "per rank (rank 0).  The march is round-latency bound (one barrier-separated round per 0.35 dnx/vmax of "
                     "travel time), not bandwidth bound; frac_seq_plus_march counts the sequential near-source kernel too; "
                     "see DESIGN.md"}
         line["e2e"] = {"value": e2e_value, "unit": "node-solves/s", "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],

@@ -85,9 +85,9 @@ int alifmm_device_count(void);
 int alifmm_create(const alifmm_model_desc *desc, int device, alifmm_ctx **out);
 void alifmm_destroy(alifmm_ctx *ctx);
 
-/* Options: "delta_frac" (acceptance band as a fraction of dnx/vmax, default 0.3, maximum
- * 0.4: measured on B200, 0.1-0.35 give the same field to rounding level on every test model,
- * 0.4 already moves homogeneous-medium edge sources by 1e-4 and 0.5 changes the solution), "handover_margin" (nodes the sequential replica runs past the last
+/* Options: "delta_frac" (acceptance band as a fraction of dnx/vmax, default 0.35, maximum 0.4: 0.1 ... 0.35 give
+ * the same bits on every test model -- the reference algorithm's own solution on a correctly ordered heap,
+ * PARITY.md --, 0.4 differs by up to 5e-12, 0.45 by 1e-7, 0.5 by 1e-4: tests/test_kernel_replay.py), "handover_margin" (nodes the sequential replica runs past the last
  * refined source box, default 27), "band_capacity_factor" (narrow-band list capacity as
  * a multiple of nz+nx of the solved grid, default 6), "threads_per_source" (CTA size of
  * the band march: 256, 512, 640, 768, 896 or 1024; default 768 = 80 registers per thread, measured

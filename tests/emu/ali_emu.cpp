@@ -34,18 +34,30 @@ extern "C" void emu_set_noise(double p, unsigned long long seed) { g_noise_p = p
 // return the same bits; the switch exists to prove it (tests/test_kernel_replay.py).
 static int g_crmath = 0;
 extern "C" void emu_set_crmath(int on) { g_crmath = on; }
-extern "C" double emu_crmath_eval(int fn, double x)   // 0 atan, 1 sin, 2 cos, 3 tan
+// fn: 0 atan, 1 sin, 2 cos, 3 tan: the literal restatements (ali_glibcmath.cuh);
+//     4 atan, 5 sin, 6 cos: the branch-light forms the kernels call (ali_glxmath.cuh)
+static double device_math(int fn, double x)
 {
-    return fn == 0 ? ali_glibc_atan(x) : fn == 1 ? ali_glibc_sin(x) : fn == 2 ? ali_glibc_cos(x) : ali_glibc_tan(x);
+    switch (fn) {
+    case 0: return ali_glibc_atan(x);
+    case 1: return ali_glibc_sin(x);
+    case 2: return ali_glibc_cos(x);
+    case 3: return ali_glibc_tan(x);
+    case 4: return ali_gx_atan(x, ali_gl_atan_cij);
+    case 5: return ali_gx_sin(x, ali_gl_sincostab);
+    default: return ali_gx_cos(x, ali_gl_sincostab);
+    }
 }
+extern "C" double emu_crmath_eval(int fn, double x) { return device_math(fn, x); }
 // Bulk comparison of the device's functions with the running libm: n arguments, returns the number of results
 // whose bits differ (NaN == NaN), and the first offending argument.
 extern "C" long long emu_math_mismatches(int fn, const double *x, long long n, double *first_bad)
 {
     long long bad = 0;
     for (long long i = 0; i < n; i++) {
-        const double a = fn == 0 ? ali_glibc_atan(x[i]) : fn == 1 ? ali_glibc_sin(x[i]) : fn == 2 ? ali_glibc_cos(x[i]) : ali_glibc_tan(x[i]);
-        const double b = fn == 0 ? atan(x[i]) : fn == 1 ? sin(x[i]) : fn == 2 ? cos(x[i]) : tan(x[i]);
+        const double a = device_math(fn, x[i]);
+        const int lf = fn >= 4 ? fn - 4 : fn;
+        const double b = lf == 0 ? atan(x[i]) : lf == 1 ? sin(x[i]) : lf == 2 ? cos(x[i]) : tan(x[i]);
         if (std::memcmp(&a, &b, 8) != 0 && !(a != a && b != b)) {
             if (bad == 0 && first_bad) *first_bad = x[i];
             bad++;
@@ -53,9 +65,9 @@ extern "C" long long emu_math_mismatches(int fn, const double *x, long long n, d
     }
     return bad;
 }
-double ali_emu_atan(double x) { return ali_emu_noise(g_crmath ? ali_glibc_atan(x) : atan(x)); }
-double ali_emu_sin(double x) { return ali_emu_noise(g_crmath ? ali_glibc_sin(x) : sin(x)); }
-double ali_emu_cos(double x) { return ali_emu_noise(g_crmath ? ali_glibc_cos(x) : cos(x)); }
+double ali_emu_atan(double x) { return ali_emu_noise(g_crmath ? ali_gx_atan(x, ali_gl_atan_cij) : atan(x)); }
+double ali_emu_sin(double x) { return ali_emu_noise(g_crmath ? ali_gx_sin(x, ali_gl_sincostab) : sin(x)); }
+double ali_emu_cos(double x) { return ali_emu_noise(g_crmath ? ali_gx_cos(x, ali_gl_sincostab) : cos(x)); }
 double ali_emu_tan(double x) { return ali_emu_noise(g_crmath ? ali_glibc_tan(x) : tan(x)); }
 
 struct HostModel {

@@ -67,7 +67,7 @@ def model_vmax(m, dnx):
     return lib().emu_model_vmax(*_margs(m, dnx))
 
 
-def ttf(m, dnx, src_iz, src_ix, sg=1, margin=27, frac=0.3, vmax=None, eager=False, level_margin=-1):
+def ttf(m, dnx, src_iz, src_ix, sg=1, margin=27, frac=0.35, vmax=None, eager=False, level_margin=-1):
     """Replays seq-init + band march for one source; m is an oracle.ali_oracle.Model."""
     if vmax is None:
         vmax = model_vmax(m, dnx)

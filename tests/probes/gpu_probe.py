@@ -14,7 +14,7 @@ from tests import models
 ap = argparse.ArgumentParser()
 ap.add_argument("--sg", type=int, default=9)
 ap.add_argument("--nsrc", type=int, default=8)
-ap.add_argument("--frac", type=float, default=0.25)
+ap.add_argument("--frac", type=float, default=0.35)
 ap.add_argument("--margin", type=int, default=27)
 ap.add_argument("--threads", type=int, default=768)
 ap.add_argument("--check", type=int, default=1, help="number of fields compared with the oracle")

@@ -3,7 +3,7 @@
 // throughput with a full device.  Dev tool:  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -fmad=false -o math_bench math_bench.cu
 #include <cstdio>
 #include <cuda_runtime.h>
-#include "../../ali_fmm_and_ray_tracing_b200/csrc/ali_glibcmath.cuh"
+#include "../../ali_fmm_and_ray_tracing_b200/csrc/ali_glxmath.cuh"
 
 template <int F> __device__ __forceinline__ double call(double x)
 {
@@ -12,6 +12,8 @@ template <int F> __device__ __forceinline__ double call(double x)
     if (F == 2) return ali_glibc_tan(x);
     if (F == 3) return ali_glibc_atan(x);
     if (F == 4) return ali_glibc_sin(x) + ali_glibc_cos(x);
+    if (F == 5) { double s, c; ali_gx_sincos(x, ali_gl_sincostab, s, c); return s + c; }
+    if (F == 6) return ali_gx_atan(x, ali_gl_atan_cij);
     if (F == 10) return sin(x);
     if (F == 11) return cos(x);
     if (F == 12) return tan(x);
@@ -61,9 +63,9 @@ int main()
 {
     run<0>("glibc sin"); run<10>("cuda sin");
     run<1>("glibc cos"); run<11>("cuda cos");
-    run<4>("glibc sin+cos"); run<14>("cuda sincos");
+    run<4>("glibc sin+cos"); run<5>("branch-light sin+cos"); run<14>("cuda sincos");
     run<2>("glibc tan"); run<12>("cuda tan");
-    run<3>("glibc atan"); run<13>("cuda atan");
+    run<3>("glibc atan"); run<6>("branch-light atan"); run<13>("cuda atan");
     run<20>("1/x"); run<21>("sqrt");
     cudaError_t e = cudaDeviceSynchronize();
     printf("status: %s\n", cudaGetErrorString(e));
