@@ -1,4 +1,4 @@
-// ali_glxmath.cuh -- branch-light forms of glibc's sin / cos / atan for SIMT hardware.
+// ali_glxmath.cuh -- branch-light forms of glibc's sin / cos / tan / atan for SIMT hardware.
 //
 // csrc/ali_glibcmath.cuh restates glibc's routines instruction by instruction, including their control
 // flow: one block of code per argument range.  On a GPU the lanes of a warp hold different angles, so
@@ -196,4 +196,57 @@ ALI_GX_DEV double ali_gx_atan(double x, const uint64_t *tab)
     const double res_c = (hp0 - ALI_GL_D(row[1])) + ALI_GL_FMA(-p, z, hp1);
     const double m = big ? res_c : res_b;
     return (u < 0.0625) ? res_a : ALI_GX_COPYSIGN(m, x);
+}
+
+// tan(x) with glibc's bits (s_tan.c).  `tab`: ali_gl_tan_xfg (186 rows of 4) or a copy of it.
+//   |x| <= 0.0608: odd polynomial;  <= 0.787: table of (x_i, tan x_i, cot x_i) at steps of 1/256 and a short
+//   series of the remainder, one division;  <= 25: x - n pi/2 in two words, then the same two cases on the
+//   reduced pair -- tan for even n, -cot for odd n (the polynomial case of -cot divides in double-double).
+// The table case -- 92 % of the angles the ray integrator produces -- is one straight line of code for every
+// range and both parities; the polynomial case (within 3.5 degrees of a multiple of 90) is a branch.
+ALI_GX_DEV double ali_gx_tan(double x, const uint64_t *tab)
+{
+    const double w = fabs(x);
+    if (!(w > ALI_GX_C(0x3e4b096c00000000)) || !(w <= 25.0)) return ali_glibc_tan_t(x, tab);   // tiny, beyond 25, nan
+    const bool small = w <= ALI_GX_C(0x3fe92f1a00000000);
+    const double toint = ALI_GX_C(0x4338000000000000);
+    const double tq = ALI_GL_FMA(x, ALI_GX_C(0x3fe45f306dc9c883), toint);
+    const double xn = tq - toint;
+    double y0 = ALI_GL_FMA(-xn, ALI_GX_C(0x3ff921fb58000000), x);
+    y0 = ALI_GL_FMA(-xn, ALI_GX_C(0xbe4dde973c000000), y0);
+    const double mp3 = ALI_GX_C(0xbc8cb3b399d747f2);
+    const double ar = ALI_GL_FMA(-xn, mp3, y0);
+    const double dar = ALI_GL_FMA(-xn, mp3, y0 - ar);
+    const double a = small ? x : ar, da = small ? 0.0 : dar;
+    const bool odd = !small && (ALI_GX_LO(tq) & 1u);
+    const double ya = fabs(a);
+    const double yya = (a < 0.0) ? -da : da, sy = (a < 0.0) ? -1.0 : 1.0;
+    if (ya <= ALI_GX_C(0x3faf212d00000000)) {
+        const double a2 = a * a;
+        double p = ALI_GL_FMA(a2, ALI_GX_C(0x3f82385a3cf2e4ea), ALI_GX_C(0x3f9664ed49cfc666));
+        p = ALI_GL_FMA(a2, p, ALI_GX_C(0x3faba1ba1cdb8745));
+        p = ALI_GL_FMA(a2, p, ALI_GX_C(0x3fc11111111107c6));
+        p = ALI_GL_FMA(a2, p, ALI_GX_C(0x3fd5555555555555));
+        const double a3 = a * a2;
+        if (small) return ALI_GL_FMA(a3, p, a);
+        const double t2 = ALI_GL_FMA(a3, p, da);
+        const double y = a + t2;
+        if (!odd) return y;
+        const double yy = (fabs(a) > fabs(t2)) ? (a - y) + t2 : (t2 - y) + a;
+        const double r = 1.0 / y;
+        const double pr = r * y;
+        const double e = ALI_GL_FMA(r, y, -pr);
+        const double s1 = ((1.0 - pr) - e) + 0.0;
+        const double q = ALI_GL_FMA(-yy, r, s1) / y;
+        const double h = r + q;
+        return -(((r - h) + q) + h);
+    }
+    const int i = (int)ALI_GL_FMA(ya, 256.0, -15.5);
+    const uint64_t *row = tab + 4 * i;
+    const double z = (ya - ALI_GL_D(row[0])) + yya;
+    const double z2 = z * z;
+    const double t = ALI_GL_FMA(z * z2, ALI_GL_FMA(z2, ALI_GX_C(0x3fc11112e0a6b45f), ALI_GX_C(0x3fd5555555554dbd)), z);
+    const double fi = ALI_GL_D(row[1]), gi = ALI_GL_D(row[2]);
+    const double d = ((fi + gi) * t) / (odd ? t + fi : gi - t);
+    return odd ? (gi - d) * -sy : (d + fi) * sy;
 }

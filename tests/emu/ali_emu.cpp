@@ -35,7 +35,7 @@ extern "C" void emu_set_noise(double p, unsigned long long seed) { g_noise_p = p
 static int g_crmath = 0;
 extern "C" void emu_set_crmath(int on) { g_crmath = on; }
 // fn: 0 atan, 1 sin, 2 cos, 3 tan: the literal restatements (ali_glibcmath.cuh);
-//     4 atan, 5 sin, 6 cos: the branch-light forms the kernels call (ali_glxmath.cuh)
+//     4 atan, 5 sin, 6 cos, 7 tan: the branch-light forms the kernels call (ali_glxmath.cuh)
 static double device_math(int fn, double x)
 {
     switch (fn) {
@@ -45,7 +45,8 @@ static double device_math(int fn, double x)
     case 3: return ali_glibc_tan(x);
     case 4: return ali_gx_atan(x, ali_gl_atan_cij);
     case 5: return ali_gx_sin(x, ali_gl_sincostab);
-    default: return ali_gx_cos(x, ali_gl_sincostab);
+    case 6: return ali_gx_cos(x, ali_gl_sincostab);
+    default: return ali_gx_tan(x, ali_gl_tan_xfg);
     }
 }
 extern "C" double emu_crmath_eval(int fn, double x) { return device_math(fn, x); }
@@ -56,7 +57,7 @@ extern "C" long long emu_math_mismatches(int fn, const double *x, long long n, d
     long long bad = 0;
     for (long long i = 0; i < n; i++) {
         const double a = device_math(fn, x[i]);
-        const int lf = fn >= 4 ? fn - 4 : fn;
+        const int lf = fn >= 4 ? fn - 4 : fn;   // 4..7 -> atan, sin, cos, tan
         const double b = lf == 0 ? atan(x[i]) : lf == 1 ? sin(x[i]) : lf == 2 ? cos(x[i]) : tan(x[i]);
         if (std::memcmp(&a, &b, 8) != 0 && !(a != a && b != b)) {
             if (bad == 0 && first_bad) *first_bad = x[i];
@@ -68,7 +69,7 @@ extern "C" long long emu_math_mismatches(int fn, const double *x, long long n, d
 double ali_emu_atan(double x) { return ali_emu_noise(g_crmath ? ali_gx_atan(x, ali_gl_atan_cij) : atan(x)); }
 double ali_emu_sin(double x) { return ali_emu_noise(g_crmath ? ali_gx_sin(x, ali_gl_sincostab) : sin(x)); }
 double ali_emu_cos(double x) { return ali_emu_noise(g_crmath ? ali_gx_cos(x, ali_gl_sincostab) : cos(x)); }
-double ali_emu_tan(double x) { return ali_emu_noise(g_crmath ? ali_glibc_tan(x) : tan(x)); }
+double ali_emu_tan(double x) { return ali_emu_noise(g_crmath ? ali_gx_tan(x, ali_gl_tan_xfg) : tan(x)); }
 
 struct HostModel {
     std::vector<AliMatRec> rec;

@@ -618,6 +618,37 @@ def test_weld_rays_py_script_workflow(capi, tmp_path):
     assert near >= 927 and exact >= 900      # (measured 944 / 935; twice the misses allowed)
 
 
+def test_parallel_methods_over_two_devices_equal_serial(capi):
+    """The thread-per-device path of the ``*_parallel`` methods (receivers sharded over the visible GPUs by
+    sharding.split_list) on TWO devices: fields, times and paths bitwise equal to the one-device run.  Needs a
+    box with at least two GPUs (gpurun --gpus 2); skipped on one."""
+    if capi.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    from Anis_TTF_rays import ALI_FMM
+    import ali_fmm_and_ray_tracing_b200.Anis_TTF_rays as shim
+    c = models.weld_crop(60, 80)
+    dnx = c["dnx"]
+    scx = dnx * np.array([5.0, 30.0, 60.0, 75.0, 20.0, 50.0])
+    scz = dnx * np.array([0.0, 0.0, 0.0, 59.0, 59.0, 59.0])
+    pairs = np.zeros((6, 6))
+    pairs[:3, 3:] = 1
+    pairs[3:, :3] = 1
+    out = {}
+    try:
+        for devs in ([0], [0, 1]):
+            shim.set_devices(devs)
+            fm = ALI_FMM(c["veln"], c["velpn"], c["vel_map"], scx, scz, stif_den=c["stif_den"], dnx=dnx)
+            T = fm.update_parallel(c["veln"], c["velpn"], c["vel_map"], stif_den=c["stif_den"], subgrid_size=3)
+            times = fm.find_all_TTF_rays_parallel(c["veln"], c["velpn"], c["vel_map"], subgrid_size=3, trans_pairs=pairs,
+                                                  stif_den=c["stif_den"], n_threads=2)
+            assert len(fm.last_counters) == len(devs) and all(k is not None for k in fm.last_counters)
+            out[len(devs)] = (T, times, np.array(fm.ray_paths_x), np.array(fm.ray_paths_y), np.array(fm.ray_len))
+    finally:
+        shim.set_devices(None)
+    for a, b in zip(out[1], out[2]):
+        assert np.array_equal(a, b)
+
+
 # ----------------------------------------------------------------------------- reference-facing API
 def test_class_api_shapes_and_conventions(capi, tmp_path, monkeypatch):
     from Anis_TTF_rays import ALI_FMM

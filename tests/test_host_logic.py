@@ -85,7 +85,7 @@ def test_material_tables_match_reference():
 
 
 def test_shard_bounds_cover_and_balance():
-    from ali_fmm_and_ray_tracing_b200.sharding import shard_bounds
+    from ali_fmm_and_ray_tracing_b200.sharding import shard_bounds, split_list
     for n in (0, 1, 7, 128, 129):
         for w in (1, 2, 3, 8):
             parts = [shard_bounds(n, w, r) for r in range(w)]
@@ -93,21 +93,38 @@ def test_shard_bounds_cover_and_balance():
             assert all(parts[i][1] == parts[i + 1][0] for i in range(w - 1))
             sizes = [b - a for a, b in parts]
             assert max(sizes) - min(sizes) <= 1
+            assert sum(split_list(list(range(n)), w), []) == list(range(n))
+
+
+def test_rank_pairs_partition_the_workload():
+    """bench.py's strong-scaling split (and the class's per-device split): every receiver and every ray of
+    the headline workload belongs to exactly one rank."""
+    from ali_fmm_and_ray_tracing_b200.sharding import rank_pairs, receivers_of
+    _, _, pairs = models.weld_headline()
+    assert receivers_of(pairs) == list(range(128))
+    for world in (1, 2, 4, 8, 3):
+        parts = [rank_pairs(pairs, world, r) for r in range(world)]
+        assert np.array_equal(sum(parts), pairs)
+        recs = [receivers_of(p) for p in parts]
+        assert sorted(sum(recs, [])) == list(range(128)) and max(map(len, recs)) - min(map(len, recs)) <= 1
+        assert all(int(p.sum()) == 64 * len(r) for p, r in zip(parts, recs))      # the rays into a receiver go with it
 
 
 def _gloo_worker(rank, world, port, q):
     import torch.distributed as dist
     import torch
-    from ali_fmm_and_ray_tracing_b200.sharding import shard_indices
+    from ali_fmm_and_ray_tracing_b200.sharding import rank_pairs, receivers_of
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
-    mine = shard_indices(13, world, rank)
-    # each rank "solves" its sources (here: records which ones) -- no collective on the data path;
-    # only the bench-style reduction of counters / times crosses ranks
+    # the product's split of a 13-transducer workload (what bench.py and ALI_FMM do per rank / device): each rank
+    # "solves" its receivers (here: records which ones) -- no collective on the data path; only the bench-style
+    # reduction of counters / times crosses ranks
+    pairs = np.triu(np.ones((13, 13)), 1) + np.tril(np.ones((13, 13)), -1)
+    mine = rank_pairs(pairs, world, rank)
     owner = torch.full((13,), -1, dtype=torch.int64)
-    owner[mine] = rank
+    owner[receivers_of(mine)] = rank
     gathered = [torch.empty_like(owner) for _ in range(world)]
     dist.all_gather(gathered, owner)
-    t = torch.tensor([float(len(mine))])
+    t = torch.tensor([float(mine.sum())])
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     tmax = torch.tensor([1.0 + rank])
     dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -119,7 +136,8 @@ def _gloo_worker(rank, world, port, q):
 
 
 def test_world_size_2_sharding_over_gloo():
-    """N > 1 path on CPU: sources are partitioned, nothing is exchanged but counters / times."""
+    """N > 1 path on CPU: receivers (and the rays into them) are partitioned by the product's sharding
+    functions, nothing is exchanged but counters / times."""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -131,7 +149,7 @@ def test_world_size_2_sharding_over_gloo():
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    assert merged == [0] * 7 + [1] * 6 and total == 13.0 and tmax == 2.0
+    assert merged == [0] * 7 + [1] * 6 and total == 13.0 * 12 and tmax == 2.0
 
 
 def test_dense_ray_arrays_behave_like_numpy_zeros():

@@ -332,14 +332,15 @@ def test_device_math_agrees_with_glibc():
     n = 10_000_000
     deg = math.pi / 180.0
     angle_sets = [rng.uniform(-2 * math.pi, 2 * math.pi, n), deg * rng.uniform(0.0, 180.0, n),
-                  deg * np.floor(rng.uniform(0.0, 361.0, n // 10)), rng.uniform(-1e3, 1e3, n // 2)]
+                  deg * np.floor(rng.uniform(0.0, 361.0, n // 10)), rng.uniform(-1e3, 1e3, n // 2),
+                  (math.pi / 2) * np.floor(rng.uniform(0, 8, n // 10)) + rng.uniform(-0.07, 0.07, n // 10)]
     atan_sets = [np.tan(rng.uniform(-1.5707, 1.5707, n)), rng.uniform(-1.0, 1.0, n), rng.uniform(-16.0, 16.0, n),
                  np.exp(rng.uniform(-60.0, 60.0, n // 2)) * rng.choice([-1.0, 1.0], n // 2)]
     special = np.array([0.0, -0.0, 1.0, -1.0, 0.5, 1e-300, -1e-300, 1e-30, 2.0 ** -27, 2.0 ** -26, 0.0625, 0.126, 0.855469,
                         2.426265, math.pi, math.pi / 2, math.pi / 4, 16.0, 1e5, 1e7, 1e18, 1e300, -1e300, np.inf, -np.inf, np.nan])
     total = 0
-    # fn 1, 2, 3: sin, cos, tan of the literal restatement; 5, 6: sin, cos of the branch-light form the kernels call
-    for fn in (1, 2, 3, 5, 6):
+    # fn 1, 2, 3: sin, cos, tan of the literal restatement; 5, 6, 7: the branch-light forms the kernels call
+    for fn in (1, 2, 3, 5, 6, 7):
         for a in angle_sets + [special[np.isfinite(special) & (np.abs(special) < 1e8)]]:
             bad, first = emu.math_mismatches(fn, a)
             assert bad == 0, (fn, bad, first)
