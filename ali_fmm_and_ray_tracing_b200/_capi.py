@@ -48,7 +48,7 @@ EXPORTS = [
     "alifmm_ttf", "alifmm_ttf_fetch", "alifmm_ttf_shape", "alifmm_rays", "alifmm_rays_into", "alifmm_trim",
     "alifmm_mem_info", "alifmm_counters",
     "alifmm_velocity_curves", "alifmm_min_max_vel", "alifmm_last_error",
-    "alifmm_velocity_curves_batch", "alifmm_eval_nodes",
+    "alifmm_velocity_curves_batch", "alifmm_eval_nodes", "alifmm_ttf_split",
 ]
 
 _lib = None
@@ -92,6 +92,8 @@ def load():
     lib.alifmm_eval_nodes.argtypes = [ctypes.c_int, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_double, _f64p,
                                       _i32p, _f64p, _i64p, ctypes.c_int32, _f64p, _f64p, ctypes.c_int32, _f64p, _i32p,
                                       _i32p, _f64p, _f64p, _i32p]
+    lib.alifmm_ttf_split.argtypes = [ctypes.POINTER(ModelDesc), ctypes.c_int32, _i32p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                     _f64p, ctypes.POINTER(Counters)]
     _lib = lib
     return lib
 
@@ -125,6 +127,26 @@ def velocity_curves_batch(materials, device=0):
     p = np.zeros((n, 361))
     _check(load().alifmm_velocity_curves_batch(int(device), n, _ptr(props, _f64p), _ptr(g, _f64p), _ptr(p, _f64p)))
     return g, p
+
+
+def ttf_split(veln, velpn, vel_map, stif_den, has_stif, group_vel, phase_vel, dnx, src_iz, src_ix, devices=(0, 1), split_row=-1):
+    """One coarse field (travel(), subgrid 1) decomposed into two row strips on two GPUs (alifmm_ttf_split).
+    Returns (field float64 [nz, nx], counters dict)."""
+    veln = np.ascontiguousarray(veln, dtype=np.float64)
+    velpn = np.ascontiguousarray(velpn, dtype=np.int32)
+    vel_map = np.ascontiguousarray(vel_map, dtype=np.float64)
+    stif = None if stif_den is None else np.ascontiguousarray(stif_den, dtype=np.int64)
+    group = np.ascontiguousarray(group_vel, dtype=np.float64)
+    phase = np.ascontiguousarray(phase_vel, dtype=np.float64)
+    nz, nx = veln.shape
+    d = ModelDesc(nz, nx, float(dnx), _ptr(veln, _f64p), _ptr(velpn, _i32p), _ptr(vel_map, _f64p), _ptr(stif, _i64p),
+                  int(bool(has_stif)), _ptr(group, _f64p), _ptr(phase, _f64p), group.shape[1])
+    dev = np.ascontiguousarray(devices, dtype=np.int32)
+    out = np.empty((nz, nx))
+    c = Counters()
+    _check(load().alifmm_ttf_split(ctypes.byref(d), len(dev), _ptr(dev, _i32p), int(src_iz), int(src_ix), int(split_row),
+                                   _ptr(out, _f64p), ctypes.byref(c)))
+    return out, c.as_dict()
 
 
 def eval_nodes(veln, velpn, vel_map, stif_den, has_stif, group_vel, phase_vel, dnx, ttn, nsts, pos, device=0):

@@ -7,7 +7,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libalifmm.so")
 SOURCES = ["alifmm.cu"]
-HEADERS = ["ali_core.cuh", "ali_seq.cuh", "ali_band.cuh", "ali_ray.cuh", "ali_glibcmath.cuh", "ali_glxmath.cuh"]
+HEADERS = ["ali_core.cuh", "ali_seq.cuh", "ali_band.cuh", "ali_ray.cuh", "ali_glibcmath.cuh", "ali_glxmath.cuh", "ali_strip.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -2071,3 +2071,252 @@ extern "C" int alifmm_eval_nodes(int device, int32_t n, int32_t nz, int32_t nx, 
     if (e != cudaSuccess) return fail(ALIFMM_E_CUDA, std::string("alifmm_eval_nodes: ") + cudaGetErrorString(e));
     return ALIFMM_OK;
 }
+
+// ---------------------------------------------------------------------------
+// one field on two GPUs: row strips with a 2-row halo over peer memory (ali_strip.cuh)
+// ---------------------------------------------------------------------------
+#include "ali_strip.cuh"
+
+namespace {
+struct StripDev {
+    int device = -1;
+    int zlo = 0, zhi = 0, za = 0, zb = 0;   // rows owned [zlo, zhi); rows allocated [za, zb) (multiples of 4, halo included)
+    cudaStream_t stream = nullptr;
+    std::vector<void *> allocs;
+    AliModel m{};
+    const AliModel *m_dev = nullptr;
+    double *Tt = nullptr; uint8_t *st = nullptr;      // allocation starts (not offset)
+    double *out = nullptr;
+    unsigned *lists = nullptr; double *stage = nullptr;
+    AliClusterCtl *ctl = nullptr; AliStripXchg *xchg = nullptr; AliSourceRec *rec = nullptr;
+    double *seq_t = nullptr; int32_t *seq_s = nullptr; int32_t *seq_heap = nullptr; double *seq_hkey = nullptr, *seq_cval = nullptr;
+    uint8_t *seq_cflag = nullptr;
+    double vmax = 0.0;
+};
+}
+
+extern "C" int alifmm_ttf_split(const alifmm_model_desc *d, int32_t n_dev, const int32_t *devices, int32_t src_iz,
+                                int32_t src_ix, int32_t split_row, double *out_host, alifmm_counters_t *counters)
+{
+    if (!d || !devices || !out_host) return fail(ALIFMM_E_INVALID, "alifmm_ttf_split: null argument");
+    if (n_dev != 2) return fail(ALIFMM_E_INVALID, "alifmm_ttf_split: exactly two devices (row strips with one boundary)");
+    if (d->nz < 64 || d->nx < 1 || !(d->dnx > 0) || !d->veln || !d->velpn || !d->vel_map || !d->group_vel || !d->phase_vel || d->n_cols < 1)
+        return fail(ALIFMM_E_INVALID, "alifmm_ttf_split: bad model descriptor (at least 64 rows)");
+    if (d->nz > 65535 || d->nx > 65535) return fail(ALIFMM_E_INVALID, "alifmm_ttf_split: grid side exceeds 65535 nodes");
+    if (src_iz < 0 || src_iz >= d->nz || src_ix < 0 || src_ix >= d->nx) return fail(ALIFMM_E_INVALID, "alifmm_ttf_split: source node outside the grid");
+    if (devices[0] == devices[1]) return fail(ALIFMM_E_INVALID, "alifmm_ttf_split: two different devices");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 2) { cudaGetLastError(); return fail(ALIFMM_E_CUDA, "alifmm_ttf_split: needs two CUDA devices"); }
+    for (int k = 0; k < 2; k++)
+        if (devices[k] < 0 || devices[k] >= ndev) return fail(ALIFMM_E_INVALID, "alifmm_ttf_split: device index out of range");
+    const int nz = d->nz, nx = d->nx, margin = 27;
+    AliSourcePlan plan;
+    AliModel pm{}; pm.nz = nz; pm.nx = nx;
+    ali_make_plan(plan, pm, src_iz, src_ix, 1, margin);
+    const int keep = plan.stop_r + 8;   // the sequential phase's window (stop_r + 4 each way) must lie inside one strip
+    int zs = split_row > 0 ? split_row : nz / 2;
+    zs &= ~3;
+    if (split_row <= 0 && abs(zs - src_iz) < keep) zs = (src_iz + keep + 3) & ~3;
+    if (split_row <= 0 && zs > nz - 8) zs = (src_iz - keep) & ~3;
+    if (zs < 8 || zs > nz - 8 || (zs > src_iz ? zs - src_iz : src_iz - zs + 1) < keep)
+        return fail(ALIFMM_E_INVALID, "alifmm_ttf_split: no admissible split row (the source's refined neighbourhood must lie inside one strip)");
+    for (size_t i = 0; i < (size_t)nz * nx; i++)
+        if (d->velpn[i] < 0 || d->velpn[i] >= d->n_cols) return fail(ALIFMM_E_INVALID, "alifmm_ttf_split: velpn holds a material id outside the velocity tables");
+
+    StripDev S[2];
+    int rc = ALIFMM_OK;
+    std::string err;
+    auto cleanup = [&]() {
+        for (StripDev &s : S) {
+            if (s.device < 0) continue;
+            cudaSetDevice(s.device);
+            if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
+            for (void *p : s.allocs) cudaFree(p);
+        }
+    };
+#define STRIP_TRY(expr)                                                                             \
+    do {                                                                                            \
+        cudaError_t e__ = (expr);                                                                   \
+        if (e__ != cudaSuccess) { err = std::string(#expr) + ": " + cudaGetErrorString(e__); cleanup(); return fail(ALIFMM_E_CUDA, "alifmm_ttf_split: " + err); } \
+    } while (0)
+    const size_t t4x = (size_t)((nx + 3) >> 2);
+    const int band_cap = (int)(6.0 * (double)(nz + nx)) + 1024;
+    const int owner = src_iz < zs ? 0 : 1;
+    size_t seq_cap = 0; int heap_cap = 0;
+    {
+        size_t lvl = ali_plan_max_level_nodes(plan);
+        size_t w = (size_t)(2 * (plan.stop_r + 4) + 1);
+        seq_cap = lvl > w * w ? lvl : w * w;
+        heap_cap = (int)(seq_cap / 2 + 64);
+    }
+    for (int k = 0; k < 2; k++) {
+        StripDev &s = S[k];
+        s.device = devices[k];
+        s.zlo = k == 0 ? 0 : zs; s.zhi = k == 0 ? zs : nz;
+        s.za = k == 0 ? 0 : zs - 4; s.zb = k == 0 ? zs + 4 : ((nz + 3) & ~3);
+        STRIP_TRY(cudaSetDevice(s.device));
+        int can = 0;
+        STRIP_TRY(cudaDeviceCanAccessPeer(&can, s.device, devices[k ^ 1]));
+        if (!can) { cleanup(); return fail(ALIFMM_E_CUDA, "alifmm_ttf_split: the two devices cannot access each other's memory"); }
+        cudaError_t pe = cudaDeviceEnablePeerAccess(devices[k ^ 1], 0);
+        if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) STRIP_TRY(pe);
+        cudaGetLastError();
+        STRIP_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        auto alloc = [&](size_t bytes, void **out) -> cudaError_t {
+            cudaError_t e = cudaMalloc(out, bytes < 256 ? 256 : bytes);
+            if (e == cudaSuccess) s.allocs.push_back(*out);
+            return e;
+        };
+        // model rows [za, min(zb, nz)) -> records
+        const int r0 = s.za, r1 = s.zb < nz ? s.zb : nz;
+        const size_t nn = (size_t)(r1 - r0) * nx, off = (size_t)r0 * nx;
+        void *dv, *dp, *dm, *ds = nullptr, *drec, *dg, *dph, *dmod, *dbad;
+        STRIP_TRY(alloc(nn * 8, &dv)); STRIP_TRY(alloc(nn * 4, &dp)); STRIP_TRY(alloc(nn * 8, &dm));
+        if (d->stif_den) STRIP_TRY(alloc(nn * 40, &ds));
+        STRIP_TRY(alloc(nn * sizeof(AliMatRec), &drec)); STRIP_TRY(alloc(64, &dbad));
+        STRIP_TRY(cudaMemcpyAsync(dv, d->veln + off, nn * 8, cudaMemcpyHostToDevice, s.stream));
+        STRIP_TRY(cudaMemcpyAsync(dp, d->velpn + off, nn * 4, cudaMemcpyHostToDevice, s.stream));
+        STRIP_TRY(cudaMemcpyAsync(dm, d->vel_map + off, nn * 8, cudaMemcpyHostToDevice, s.stream));
+        if (ds) STRIP_TRY(cudaMemcpyAsync(ds, d->stif_den + off * 5, nn * 40, cudaMemcpyHostToDevice, s.stream));
+        STRIP_TRY(cudaMemsetAsync(dbad, 0, 64, s.stream));
+        {
+            int blocks = (int)((nn + 255) / 256);
+            if (blocks > 148 * 8) blocks = 148 * 8;
+            ali_records_kernel<<<blocks, 256, 0, s.stream>>>((int)nn, (const double *)dv, (const int32_t *)dp, (const double *)dm,
+                                                            (const long long *)ds, (AliMatRec *)drec, (int *)dbad);
+        }
+        STRIP_TRY(alloc((size_t)361 * d->n_cols * 8, &dg)); STRIP_TRY(alloc((size_t)361 * d->n_cols * 8, &dph));
+        STRIP_TRY(cudaMemcpyAsync(dg, d->group_vel, (size_t)361 * d->n_cols * 8, cudaMemcpyHostToDevice, s.stream));
+        STRIP_TRY(cudaMemcpyAsync(dph, d->phase_vel, (size_t)361 * d->n_cols * 8, cudaMemcpyHostToDevice, s.stream));
+        // the strip's own maximum of the phase velocity (on its rows, with a strip-local model view)
+        AliModel ml{};
+        ml.nz = r1 - r0; ml.nx = nx; ml.rec = (const AliMatRec *)drec; ml.has_stif = d->has_stif ? 1 : 0;
+        ml.group_tab = (const double *)dg; ml.phase_tab = (const double *)dph; ml.ncol = d->n_cols; ml.dnx = d->dnx;
+        unsigned long long *dvmax = (unsigned long long *)dbad + 1;
+        {
+            int blocks = (int)((nn + 255) / 256);
+            if (blocks > 148 * 8) blocks = 148 * 8;
+            ali_vmax_kernel<<<blocks, 256, 0, s.stream>>>(ml, dvmax);
+        }
+        unsigned long long hb[2] = {0, 0};
+        STRIP_TRY(cudaMemcpyAsync(hb, dbad, 16, cudaMemcpyDeviceToHost, s.stream));
+        STRIP_TRY(cudaStreamSynchronize(s.stream));
+        if ((int)hb[0]) { cleanup(); return fail(ALIFMM_E_INVALID, "alifmm_ttf_split: veln / vel_map hold non-finite values"); }
+        memcpy(&s.vmax, &hb[1], 8);
+        // the march's model: full-grid extents, records offset so that (z * nx + x) indexes the strip's rows
+        s.m = ml; s.m.nz = nz; s.m.rec = (const AliMatRec *)drec - off;
+        STRIP_TRY(alloc(sizeof(AliModel), &dmod));
+        STRIP_TRY(cudaMemcpyAsync(dmod, &s.m, sizeof(AliModel), cudaMemcpyHostToDevice, s.stream));
+        s.m_dev = (const AliModel *)dmod;
+        // field strip (tiled), alive flags, result rows, lists, control / exchange blocks, record
+        const size_t tn = (size_t)((s.zb - s.za) >> 2) * t4x * 16;
+        STRIP_TRY(alloc(tn * 8, (void **)&s.Tt)); STRIP_TRY(alloc(tn + 16, (void **)&s.st));
+        STRIP_TRY(alloc((size_t)(s.zhi - s.zlo) * nx * 8, (void **)&s.out));
+        STRIP_TRY(alloc((size_t)4 * band_cap * 4, (void **)&s.lists)); STRIP_TRY(alloc((size_t)2 * band_cap * 8, (void **)&s.stage));
+        STRIP_TRY(alloc(sizeof(AliClusterCtl), (void **)&s.ctl)); STRIP_TRY(alloc(sizeof(AliStripXchg), (void **)&s.xchg));
+        STRIP_TRY(alloc(sizeof(AliSourceRec), (void **)&s.rec));
+        STRIP_TRY(cudaMemsetAsync(s.Tt, ALI_T_UNSET_BYTE, tn * 8, s.stream));
+        STRIP_TRY(cudaMemsetAsync(s.st, 0, tn + 16, s.stream));
+        STRIP_TRY(cudaMemsetAsync(s.ctl, 0, sizeof(AliClusterCtl), s.stream));
+        STRIP_TRY(cudaMemsetAsync(s.xchg, 0, sizeof(AliStripXchg), s.stream));
+        AliSourceRec hr;
+        memset(&hr, 0, sizeof hr);
+        hr.src_iz = src_iz; hr.src_ix = src_ix;
+        STRIP_TRY(cudaMemcpyAsync(s.rec, &hr, sizeof hr, cudaMemcpyHostToDevice, s.stream));
+        if (k == owner) {
+            STRIP_TRY(alloc(2 * seq_cap * 8, (void **)&s.seq_t)); STRIP_TRY(alloc(2 * seq_cap * 4, (void **)&s.seq_s));
+            STRIP_TRY(alloc((size_t)2 * heap_cap * 4, (void **)&s.seq_heap)); STRIP_TRY(alloc(ALI_HKEY_SLOTS(heap_cap) * 8, (void **)&s.seq_hkey));
+            STRIP_TRY(alloc(seq_cap * 8, (void **)&s.seq_cval)); STRIP_TRY(alloc(seq_cap + 16, (void **)&s.seq_cflag));
+        }
+        STRIP_TRY(cudaStreamSynchronize(s.stream));
+    }
+    const double vmax = S[0].vmax > S[1].vmax ? S[0].vmax : S[1].vmax;
+    if (!(vmax > 0) || !isfinite(vmax)) { cleanup(); return fail(ALIFMM_E_INVALID, "alifmm_ttf_split: model has no positive finite phase velocity"); }
+    AliStripArgs A[2];
+    for (int k = 0; k < 2; k++) {
+        StripDev &s = S[k];
+        AliBatch &b = A[k].b;
+        memset(&b, 0, sizeof b);
+        b.m = s.m; b.m_dev = s.m_dev; b.sg = 1; b.nz = nz; b.nx = nx; b.margin = margin;
+        b.delta = 0.35 * d->dnx / vmax;
+        b.Tt = s.Tt - (size_t)(s.za >> 2) * t4x * 16;
+        b.st = s.st - (size_t)(s.za >> 2) * t4x * 16;
+        b.tn = 0;
+        b.seq_t = s.seq_t; b.seq_s = s.seq_s; b.seq_heap = s.seq_heap; b.seq_hkey = s.seq_hkey; b.seq_cval = s.seq_cval; b.seq_cflag = s.seq_cflag;
+        b.seq_cap = seq_cap; b.heap_cap = heap_cap;
+        b.lists = s.lists; b.stage = s.stage; b.band_cap = band_cap; b.resort_every = 8; b.rec = s.rec;
+        A[k].ctl = s.ctl; A[k].xl = s.xchg; A[k].zlo = s.zlo; A[k].zhi = s.zhi; A[k].has_seq = k == owner;
+        A[k].spin_limit = 400000000LL;   // ~ a minute of 64 ns sleeps: a dead peer ends the kernel instead of hanging the GPU
+    }
+    for (int k = 0; k < 2; k++) {
+        const StripDev &p = S[k ^ 1];
+        A[k].pT = p.Tt - (size_t)(p.za >> 2) * t4x * 16;
+        A[k].pst = p.st - (size_t)(p.za >> 2) * t4x * 16;
+        A[k].pctl = p.ctl; A[k].px = p.xchg; A[k].plists = p.lists; A[k].pstage = p.stage;
+    }
+    cudaEvent_t ev[3];
+    STRIP_TRY(cudaSetDevice(S[owner].device));
+    for (auto &e : ev) STRIP_TRY(cudaEventCreate(&e));
+    STRIP_TRY(cudaEventRecord(ev[0], S[owner].stream));
+    ali_seq_kernel<<<1, 32, 0, S[owner].stream>>>(A[owner].b);
+    STRIP_TRY(cudaGetLastError());
+    STRIP_TRY(cudaEventRecord(ev[1], S[owner].stream));
+    STRIP_TRY(cudaStreamSynchronize(S[owner].stream));
+    for (int k = 0; k < 2; k++) {
+        STRIP_TRY(cudaSetDevice(S[k].device));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(8); cfg.blockDim = dim3(512);
+        cfg.dynamicSmemBytes = (size_t)ALI_MT_WORDS * 8; cfg.stream = S[k].stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 8; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        STRIP_TRY(cudaLaunchKernelEx(&cfg, ali_march_strip_kernel<512>, A[k]));
+    }
+    AliSourceRec recs[2];
+    for (int k = 0; k < 2; k++) {
+        STRIP_TRY(cudaSetDevice(S[k].device));
+        if (k == owner) STRIP_TRY(cudaEventRecord(ev[2], S[k].stream));
+        const size_t total = (size_t)(S[k].zhi - S[k].zlo) * nx;
+        int blocks = (int)((total + 255) / 256);
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        ali_finalize_rows_kernel<<<blocks, 256, 0, S[k].stream>>>(A[k].b.Tt, A[k].b.st, S[k].out, S[k].zlo, S[k].zhi, nx);
+        STRIP_TRY(cudaMemcpyAsync(&recs[k], S[k].rec, sizeof(AliSourceRec), cudaMemcpyDeviceToHost, S[k].stream));
+    }
+    for (int k = 0; k < 2; k++) {
+        STRIP_TRY(cudaSetDevice(S[k].device));
+        STRIP_TRY(cudaStreamSynchronize(S[k].stream));
+    }
+    const int ovf = recs[0].overflow | recs[1].overflow;
+    if (ovf) {
+        cleanup();
+        if (ovf & 4) return fail(ALIFMM_E_CUDA, "alifmm_ttf_split: a GPU stopped answering the per-round exchange");
+        if (ovf & 2) return fail(ALIFMM_E_CAPACITY, "alifmm_ttf_split: narrow-band list overflowed");
+        return fail(ALIFMM_E_CAPACITY, "alifmm_ttf_split: sequential near-source scratch overflowed");
+    }
+    for (int k = 0; k < 2; k++) {
+        STRIP_TRY(cudaSetDevice(S[k].device));
+        STRIP_TRY(cudaMemcpy(out_host + (size_t)S[k].zlo * nx, S[k].out, (size_t)(S[k].zhi - S[k].zlo) * nx * 8, cudaMemcpyDeviceToHost));
+    }
+    if (counters) {
+        memset(counters, 0, sizeof *counters);
+        float ms = 0;
+        cudaSetDevice(S[owner].device);
+        cudaEventElapsedTime(&ms, ev[0], ev[1]); counters->ms_seq = ms;
+        cudaEventElapsedTime(&ms, ev[1], ev[2]); counters->ms_march = ms;
+        counters->node_solves = (int64_t)nz * nx;
+        counters->seq_pops = recs[owner].seq.cnt.pops; counters->seq_evals = recs[owner].seq.cnt.evals;
+        counters->band_rounds = counters->band_rounds_max = recs[0].rounds;
+        counters->band_evals = recs[0].band_evals + recs[1].band_evals;
+        counters->fallback_evals = recs[owner].seq.cnt.fallbacks + recs[0].band_fallbacks + recs[1].band_fallbacks;
+        counters->max_band = recs[0].max_band + recs[1].max_band;
+        counters->kernel_launches = 5;
+        counters->vmax = vmax; counters->delta = 0.35 * d->dnx / vmax;
+        counters->cluster_size = 8; counters->seq_threads = 32;
+    }
+    cudaSetDevice(S[owner].device);
+    for (auto &e : ev) cudaEventDestroy(e);
+    cleanup();
+#undef STRIP_TRY
+    return ALIFMM_OK;
+}

@@ -649,6 +649,38 @@ def test_parallel_methods_over_two_devices_equal_serial(capi):
         assert np.array_equal(a, b)
 
 
+def test_two_gpu_strips_equal_one_gpu(capi):
+    """one coarse field decomposed into two row strips on two GPUs (2-row halo, claims and the
+    per-round minimum exchanged through peer memory) against the same field solved on one GPU: every bit equal.
+    Sources in either strip, automatic and explicit split rows, a Voronoi grid (closed fronts crossing the boundary
+    both ways) and config 5's long extent.  Needs two GPUs (gpurun --gpus 2); skipped on one."""
+    if capi.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    nz, nx = 16384, 192
+    rng = np.random.default_rng(11)
+    veln = np.repeat(np.repeat(rng.uniform(0, 180, (nz // 64, nx // 64)), 64, axis=0), 64, axis=1)
+    long_m = dict(veln=veln, velpn=np.zeros((nz, nx), dtype=int), vel_map=np.ones((nz, nx)),
+                  stif_den=models.const_stif((nz, nx)), dnx=1e-4)
+    cases = [(models.voronoi(768, 120, 77), [((100, 300), -1), ((700, 40), -1), ((384, 384), -1), ((10, 10), 600), ((767, 767), 64)]),
+             (models.weld_crop(200, 260), [((0, 130), -1), ((199, 20), 100)]),
+             (long_m, [((8192, 96), -1), ((100, 3), 12000)])]
+    for m, runs in cases:
+        g, p = _tables(m)
+        ctx = _ctx(capi, m)
+        for (sz, sx), split in runs:
+            one = ctx.ttf(np.array([sz], dtype=np.int32), np.array([sx], dtype=np.int32), 1)[0]
+            c1 = ctx.counters()
+            two, c2 = capi.ttf_split(m["veln"], m["velpn"], m["vel_map"], m["stif_den"], True, g, p, m["dnx"], sz, sx,
+                                     devices=(0, 1), split_row=split)
+            assert np.array_equal(one, two), (m["veln"].shape, sz, sx, split, models.rel_err(one, two).max())
+            assert c2["band_rounds"] == c1["band_rounds"] and c2["band_evals"] == c1["band_evals"], (c1, c2)
+        ctx.close()
+    with pytest.raises(RuntimeError):   # the source's refined neighbourhood would straddle the boundary
+        m = cases[0][0]
+        g, p = _tables(m)
+        capi.ttf_split(m["veln"], m["velpn"], m["vel_map"], m["stif_den"], True, g, p, m["dnx"], 384, 384, split_row=380)
+
+
 # ----------------------------------------------------------------------------- reference-facing API
 def test_class_api_shapes_and_conventions(capi, tmp_path, monkeypatch):
     from Anis_TTF_rays import ALI_FMM
