@@ -673,7 +673,10 @@ def test_two_gpu_strips_equal_one_gpu(capi):
             two, c2 = capi.ttf_split(m["veln"], m["velpn"], m["vel_map"], m["stif_den"], True, g, p, m["dnx"], sz, sx,
                                      devices=(0, 1), split_row=split)
             assert np.array_equal(one, two), (m["veln"].shape, sz, sx, split, models.rel_err(one, two).max())
-            assert c2["band_rounds"] == c1["band_rounds"] and c2["band_evals"] == c1["band_evals"], (c1, c2)
+            # same rounds; never more evaluations (the window-change bitmap is folded 512 x 512, and a strip's bitmap
+            # only receives its own marks and the boundary's: fewer aliases, so fewer value-preserving re-evaluations)
+            assert c2["band_rounds"] == c1["band_rounds"], (c1, c2)
+            assert 0.99 * c1["band_evals"] <= c2["band_evals"] <= c1["band_evals"], (c1["band_evals"], c2["band_evals"])
         ctx.close()
     with pytest.raises(RuntimeError):   # the source's refined neighbourhood would straddle the boundary
         m = cases[0][0]
