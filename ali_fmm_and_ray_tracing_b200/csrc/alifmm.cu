@@ -18,6 +18,7 @@
 #include <stdlib.h>
 #include <string>
 #include <vector>
+#include <algorithm>
 #include <mutex>
 #include <thread>
 
@@ -906,6 +907,8 @@ struct AliRayArgs {
     const double *T;            // resident fields
     const AliSourceRec *rec;    // their sources
     const AliRayJob *jobs;
+    const int *order;           // ray indices, longest expected path first
+    int *next;                  // work queue: next position in `order`
     int n_rays, cap;
     double *out_x, *out_y, *out_time;
     int *out_len, *out_flag;
@@ -913,80 +916,91 @@ struct AliRayArgs {
 };
 
 #define ALI_RAY_WARPS 4
-__global__ void __launch_bounds__(32 * ALI_RAY_WARPS) ali_rays_kernel(AliRayArgs a)
+template <int MINB>
+__global__ void __launch_bounds__(32 * ALI_RAY_WARPS, MINB) ali_rays_kernel(AliRayArgs a)
 {
     extern __shared__ double s_buf[];
     __shared__ AliRayState s_state[ALI_RAY_WARPS];
     __shared__ AliRayPlane s_plane[ALI_RAY_WARPS];
     __shared__ int s_go[ALI_RAY_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ray = blockIdx.x * ALI_RAY_WARPS + warp;
-    if (ray >= a.n_rays) return;
-    double *TT = s_buf + (size_t)warp * 3 * a.maxc;
-    double *vals = TT + a.maxc;
-    double *poss = vals + a.maxc;
-    AliRayState &s = s_state[warp];
-    AliRayPlane &pl = s_plane[warp];
-    const AliRayJob job = a.jobs[ray];
-    const double *rec = a.T + (size_t)job.rec_slot * a.fz * a.fx;
-    double *ray_x = a.out_x + (size_t)ray * a.cap;
-    double *ray_y = a.out_y + (size_t)ray * a.cap;
-    if (lane == 0) {
-        const AliSourceRec &r = a.rec[job.rec_slot];
-        s.last_x = (double)(a.sg * job.src_ix); s.last_y = (double)(a.sg * job.src_iz);
-        s.rx = (double)(a.sg * r.src_ix); s.ry = (double)(a.sg * r.src_iz);
-        s.lvx = s.rx - s.last_x; s.lvy = s.ry - s.last_y;
-        s.len = 1; s.flag = 0; s.done = 0;
-        ray_x[0] = s.last_x; ray_y[0] = s.last_y;
-    }
-    __syncwarp();
-    while (true) {
+    // The warps take rays from a queue ordered longest-first (paths differ 2x in length: a fixed ray -> warp
+    // assignment left the SMs half empty while the longest rays of the last wave finished).
+    for (;;) {
+        int ray = 0;
         if (lane == 0) {
-            int go = 0;
-            if (ali_ray_continue(s, a.sg)) {
-                if (s.len >= a.cap - 1) s.flag |= ALI_RAY_CAPACITY;
-                else go = ali_ray_choose_plane(s, a.sg, a.fz, a.fx, pl) ? 1 : 0;
+            const int q = atomicAdd(a.next, 1);
+            ray = q < a.n_rays ? a.order[q] : -1;
+        }
+        ray = __shfl_sync(0xffffffffu, ray, 0);
+        if (ray < 0) break;
+        double *TT = s_buf + (size_t)warp * 3 * a.maxc;
+        double *vals = TT + a.maxc;
+        double *poss = vals + a.maxc;
+        AliRayState &s = s_state[warp];
+        AliRayPlane &pl = s_plane[warp];
+        const AliRayJob job = a.jobs[ray];
+        const double *rec = a.T + (size_t)job.rec_slot * a.fz * a.fx;
+        double *ray_x = a.out_x + (size_t)ray * a.cap;
+        double *ray_y = a.out_y + (size_t)ray * a.cap;
+        if (lane == 0) {
+            const AliSourceRec &r = a.rec[job.rec_slot];
+            s.last_x = (double)(a.sg * job.src_ix); s.last_y = (double)(a.sg * job.src_iz);
+            s.rx = (double)(a.sg * r.src_ix); s.ry = (double)(a.sg * r.src_iz);
+            s.lvx = s.rx - s.last_x; s.lvy = s.ry - s.last_y;
+            s.len = 1; s.flag = 0; s.done = 0;
+            ray_x[0] = s.last_x; ray_y[0] = s.last_y;
+        }
+        __syncwarp();
+        while (true) {
+            if (lane == 0) {
+                int go = 0;
+                if (ali_ray_continue(s, a.sg)) {
+                    if (s.len >= a.cap - 1) s.flag |= ALI_RAY_CAPACITY;
+                    else go = ali_ray_choose_plane(s, a.sg, a.fz, a.fx, pl) ? 1 : 0;
+                }
+                s_go[warp] = go;
             }
-            s_go[warp] = go;
+            __syncwarp();
+            if (!s_go[warp]) break;
+            const double lx = s.last_x, ly = s.last_y;
+            for (int i = lane; i < pl.len; i += 32) TT[i] = ali_ray_candidate_time(a.m, rec, a.fx, pl, i, lx, ly, a.sg);
+            __syncwarp();
+            for (int j = 1 + lane; j < pl.len - 1; j += 32) vals[j] = ali_ray_local_min(TT, j, poss[j]);
+            __syncwarp();
+            if (lane == 0) {
+                double min_i = ali_ray_select(TT, vals, poss, pl.len);
+                s_go[warp] = ali_ray_advance(s, pl, min_i, rec, a.fx, ray_x, ray_y) ? 1 : 0;
+            }
+            __syncwarp();
+            if (!s_go[warp]) break;
         }
-        __syncwarp();
-        if (!s_go[warp]) break;
-        const double lx = s.last_x, ly = s.last_y;
-        for (int i = lane; i < pl.len; i += 32) TT[i] = ali_ray_candidate_time(a.m, rec, a.fx, pl, i, lx, ly, a.sg);
-        __syncwarp();
-        for (int j = 1 + lane; j < pl.len - 1; j += 32) vals[j] = ali_ray_local_min(TT, j, poss[j]);
-        __syncwarp();
         if (lane == 0) {
-            double min_i = ali_ray_select(TT, vals, poss, pl.len);
-            s_go[warp] = ali_ray_advance(s, pl, min_i, rec, a.fx, ray_x, ray_y) ? 1 : 0;
+            ray_x[s.len] = s.rx; ray_y[s.len] = s.ry;
+            s.len += 1;
         }
         __syncwarp();
-        if (!s_go[warp]) break;
-    }
-    if (lane == 0) {
-        ray_x[s.len] = s.rx; ray_y[s.len] = s.ry;
-        s.len += 1;
-    }
-    __syncwarp();
-    // ray_time (ATR:2992-3022): segment times in parallel, summed in path order
-    const int nseg = s.len - 1;
-    double acc = 0.0;
-    for (int base = 0; base < nseg; base += 32) {
-        int i = base + lane;
-        double v = 0.0;
-        if (i < nseg) v = ali_time_between_points(a.m, ray_x[i], ray_x[i + 1], ray_y[i], ray_y[i + 1], a.sg, 1 << 20);
-        TT[lane] = v;
-        __syncwarp();
+        // ray_time (ATR:2992-3022): segment times in parallel, summed in path order
+        const int nseg = s.len - 1;
+        double acc = 0.0;
+        for (int base = 0; base < nseg; base += 32) {
+            int i = base + lane;
+            double v = 0.0;
+            if (i < nseg) v = ali_time_between_points(a.m, ray_x[i], ray_x[i + 1], ray_y[i], ray_y[i + 1], a.sg, 1 << 20);
+            TT[lane] = v;
+            __syncwarp();
+            if (lane == 0) {
+                int cnt = nseg - base < 32 ? nseg - base : 32;
+                for (int q = 0; q < cnt; q++) acc += TT[q];
+            }
+            __syncwarp();
+        }
         if (lane == 0) {
-            int cnt = nseg - base < 32 ? nseg - base : 32;
-            for (int q = 0; q < cnt; q++) acc += TT[q];
+            a.out_len[ray] = s.len;
+            a.out_time[ray] = acc;
+            a.out_flag[ray] = s.flag;
         }
         __syncwarp();
-    }
-    if (lane == 0) {
-        a.out_len[ray] = s.len;
-        a.out_time[ray] = acc;
-        a.out_flag[ray] = s.flag;
     }
 }
 
@@ -1131,13 +1145,15 @@ struct alifmm_ctx {
     double band_cap_factor = 6.0;
     int threads_per_source = 768;   // 80 registers per thread: fewer spills than 1024 x 64, more warps than 512 x 128 (measured)
     int resort_every = 8;
+    int ray_min_blocks = 4;     // CTAs of 4 warps per SM the ray kernel is compiled for (4: 126 registers, 5: 102, 6: 85)
     int band_smem_bytes = 0;   // measured on B200: L1 for the T / status gathers is worth more than smem lists
     int seq_threads = 32;      // CTA size of the sequential near-source kernel: 32 = one warp (measured fastest); 64..256 = one candidate per warp
     int cluster_size = 0;      // CTAs (SMs) per source in the band march: 0 = as many (1, 2, 4, 8) as keep the batch in one wave
     int cluster_threads = 0;   // CTA size of the cluster march: 0 = 512 (128 registers, no spills), else 512 or 768
     // resident batch
     int n_slots = 0, sg = 0, fz = 0, fx = 0;
-    DevBuf T, Tt, st, seq_t, seq_s, seq_heap, seq_hkey, seq_cval, seq_cflag, lists, stage, rec, jobs, ray_x, ray_y, ray_time, ray_len, ray_flag, ray_off, pack, misc, ctl;
+    std::vector<int> slot_iz, slot_ix;   // source node of every resident field
+    DevBuf T, Tt, st, seq_t, seq_s, seq_heap, seq_hkey, seq_cval, seq_cflag, lists, stage, rec, jobs, ray_q, ray_x, ray_y, ray_time, ray_len, ray_flag, ray_off, pack, misc, ctl;
     alifmm_counters_t cnt{};
 };
 
@@ -1350,7 +1366,7 @@ extern "C" void alifmm_destroy(alifmm_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (DevBuf &mb : c->model_allocs) dev_release(mb, c->device);
-    DevBuf *bufs[] = {&c->T, &c->Tt, &c->st, &c->seq_t, &c->seq_s, &c->seq_heap, &c->seq_hkey, &c->seq_cval, &c->seq_cflag, &c->lists, &c->stage, &c->rec, &c->jobs,
+    DevBuf *bufs[] = {&c->T, &c->Tt, &c->st, &c->seq_t, &c->seq_s, &c->seq_heap, &c->seq_hkey, &c->seq_cval, &c->seq_cflag, &c->lists, &c->stage, &c->rec, &c->jobs, &c->ray_q,
                       &c->ray_x, &c->ray_y, &c->ray_time, &c->ray_len, &c->ray_flag, &c->ray_off, &c->pack, &c->misc, &c->ctl};
     for (DevBuf *b : bufs) dev_release(*b, c->device);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
@@ -1472,6 +1488,9 @@ extern "C" int alifmm_set_option(alifmm_ctx *c, const char *name, double value)
         if (t != 256 && t != 512 && t != 640 && t != 768 && t != 896 && t != 1024)
             return fail(ALIFMM_E_INVALID, "threads_per_source must be 256, 512, 640, 768, 896 or 1024");
         c->threads_per_source = t;
+    } else if (!strcmp(name, "ray_min_blocks")) {
+        if (value != 4 && value != 5 && value != 6) return fail(ALIFMM_E_INVALID, "alifmm_set_option: ray_min_blocks is 4, 5 or 6");
+        c->ray_min_blocks = (int)value;
     } else if (!strcmp(name, "resort_every")) {
         if (value < 0 || value > 1000000) return fail(ALIFMM_E_INVALID, "resort_every must be >= 0");
         c->resort_every = (int)value;
@@ -1574,6 +1593,7 @@ static int ttf_attempt(alifmm_ctx *c, int32_t n_src, const int32_t *src_iz, cons
     memset(recs.data(), 0, recs.size() * sizeof(AliSourceRec));
     for (int k = 0; k < n_src; k++) { recs[k].src_iz = src_iz[k]; recs[k].src_ix = src_ix[k]; }
     c->n_slots = 0;
+    c->slot_iz.assign(src_iz, src_iz + n_src); c->slot_ix.assign(src_ix, src_ix + n_src);
     cudaStream_t s = c->stream;
     CUDA_TRY(cudaMemcpyAsync(b.rec, recs.data(), recs.size() * sizeof(AliSourceRec), cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaEventRecord(c->ev[0], s));
@@ -1753,9 +1773,22 @@ static int rays_launch(alifmm_ctx *c, int32_t n_rays, const int32_t *src_iz, con
             return fail(ALIFMM_E_INVALID, "alifmm_rays: source node outside the grid");
         jobs[r].src_iz = src_iz[r]; jobs[r].src_ix = src_ix[r]; jobs[r].rec_slot = rec_slot[r];
     }
+    // longest expected path first (distance source -> receiver)
+    std::vector<int> order(n_rays + 1);
+    {
+        std::vector<long long> key(n_rays);
+        for (int r = 0; r < n_rays; r++) {
+            const long long dz = src_iz[r] - c->slot_iz[rec_slot[r]], dx = src_ix[r] - c->slot_ix[rec_slot[r]];
+            key[r] = dz * dz + dx * dx;
+            order[r + 1] = r;
+        }
+        std::stable_sort(order.begin() + 1, order.end(), [&](int p, int q) { return key[p] > key[q]; });
+        order[0] = 0;   // the queue's counter
+    }
     CUDA_TRY(cudaSetDevice(c->device));
     int rc;
     if ((rc = dev_reserve(c->jobs, (size_t)n_rays * sizeof(AliRayJob))) != 0) return rc;
+    if ((rc = dev_reserve(c->ray_q, (size_t)(n_rays + 1) * sizeof(int))) != 0) return rc;
     if ((rc = dev_reserve(c->ray_x, (size_t)n_rays * cap * sizeof(double))) != 0) return rc;
     if ((rc = dev_reserve(c->ray_y, (size_t)n_rays * cap * sizeof(double))) != 0) return rc;
     if ((rc = dev_reserve(c->ray_time, (size_t)n_rays * sizeof(double))) != 0) return rc;
@@ -1763,6 +1796,7 @@ static int rays_launch(alifmm_ctx *c, int32_t n_rays, const int32_t *src_iz, con
     if ((rc = dev_reserve(c->ray_flag, (size_t)n_rays * sizeof(int))) != 0) return rc;
     a.m = c->m; a.sg = c->sg; a.fz = c->fz; a.fx = c->fx;
     a.T = (const double *)c->T.p; a.rec = (const AliSourceRec *)c->rec.p; a.jobs = (const AliRayJob *)c->jobs.p;
+    a.next = (int *)c->ray_q.p; a.order = a.next + 1;
     a.n_rays = n_rays; a.cap = cap;
     a.out_x = (double *)c->ray_x.p; a.out_y = (double *)c->ray_y.p; a.out_time = (double *)c->ray_time.p;
     a.out_len = (int *)c->ray_len.p; a.out_flag = (int *)c->ray_flag.p;
@@ -1770,18 +1804,28 @@ static int rays_launch(alifmm_ctx *c, int32_t n_rays, const int32_t *src_iz, con
     if (a.maxc < 32) a.maxc = 32;
     cudaStream_t s = c->stream;
     CUDA_TRY(cudaMemcpyAsync(c->jobs.p, jobs.data(), jobs.size() * sizeof(AliRayJob), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(c->ray_q.p, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice, s));
     // (pageable source: the call returns once `jobs` has been staged)
     const size_t smem = (size_t)ALI_RAY_WARPS * 3 * a.maxc * sizeof(double);
-    if (smem > 48 * 1024) {
-        if (smem > 200 * 1024) return fail(ALIFMM_E_INVALID, "alifmm_rays: subgrid too large for the ray kernel's shared memory");
-        CUDA_TRY(cudaFuncSetAttribute(ali_rays_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    }
+    if (smem > 200 * 1024) return fail(ALIFMM_E_INVALID, "alifmm_rays: subgrid too large for the ray kernel's shared memory");
+    void (*kern)(AliRayArgs) = c->ray_min_blocks >= 6 ? ali_rays_kernel<6> : c->ray_min_blocks == 5 ? ali_rays_kernel<5> : ali_rays_kernel<4>;
+    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (zero_paths) {   // the whole [n_rays][cap] block goes to the caller: no stale bytes of a recycled buffer behind a path
         CUDA_TRY(cudaMemsetAsync(a.out_x, 0, (size_t)n_rays * cap * sizeof(double), s));
         CUDA_TRY(cudaMemsetAsync(a.out_y, 0, (size_t)n_rays * cap * sizeof(double), s));
     }
     CUDA_TRY(cudaEventRecord(c->ev[3], s));
-    ali_rays_kernel<<<(n_rays + ALI_RAY_WARPS - 1) / ALI_RAY_WARPS, 32 * ALI_RAY_WARPS, smem, s>>>(a);
+    int blocks = (n_rays + ALI_RAY_WARPS - 1) / ALI_RAY_WARPS;
+    {   // no more CTAs than fit at once: the rest of the rays come through the queue
+        int per_sm = 0, sms = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * ALI_RAY_WARPS, smem) == cudaSuccess &&
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device) == cudaSuccess && per_sm > 0 && sms > 0) {
+            if (blocks > per_sm * sms) blocks = per_sm * sms;
+        } else {
+            cudaGetLastError();
+        }
+    }
+    kern<<<blocks, 32 * ALI_RAY_WARPS, smem, s>>>(a);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(c->ev[4], s));
     return ALIFMM_OK;

@@ -65,11 +65,17 @@ if a.check:
 if a.rays:
     rng = np.random.default_rng(0)
     rs = rng.integers(0, n, a.rays); rr = (rs + 1 + rng.integers(0, n - 1, a.rays)) % n
-    t0 = time.time()
-    x, y, ln, tm, fl = ctx.rays(iz[rs], ix[rs], rr.astype(np.int32))
-    dt = time.time() - t0
-    c = ctx.counters()
-    print("rays wall %.3f s kernel %.1f ms: %d rays, %d points, flags %s" % (dt, c["ms_rays"], a.rays, ln.sum(), np.bincount(fl)), flush=True)
+    keep = None
+    for mb in (4, 5, 6, 4):
+        ctx.set_option("ray_min_blocks", mb)
+        t0 = time.time()
+        x, y, ln, tm, fl = ctx.rays(iz[rs], ix[rs], rr.astype(np.int32))
+        dt = time.time() - t0
+        c = ctx.counters()
+        same = "" if keep is None else " same as first: %s" % (np.array_equal(keep[0], x) and np.array_equal(keep[1], tm) and np.array_equal(keep[2], ln))
+        if keep is None:
+            keep = (x.copy(), tm.copy(), ln.copy())
+        print("rays (min blocks %d) wall %.3f s kernel %.1f ms: %d rays, %d points, flags %s%s" % (mb, dt, c["ms_rays"], a.rays, ln.sum(), np.bincount(fl), same), flush=True)
     if a.check:
         for r in range(min(3, a.rays)):
             T = ctx.ttf_fetch(int(rr[r]))
