@@ -214,8 +214,10 @@ ALI_DEV int ali_band_accept(const AliBandGrid &g, int iz, int ix, unsigned *nb)
         nw = me - 1; ne = me + 1; nn = me - g.nx; ns = me + g.nx;
     }
 #if defined(__CUDA_ARCH__)
-    // the four state words are loaded together (one memory latency), then only far ones are claimed
-    const volatile unsigned long long *tw = (const volatile unsigned long long *)g.T;
+    // The four state words are loaded together (one memory latency), then only far ones are claimed.  Plain
+    // (L1-cached) loads: the lines are usually still there from phase A's gathers, and a stale word can only
+    // read "far" for a node that has been claimed since (states never return to far) -- the CAS settles that.
+    const unsigned long long *tw = (const unsigned long long *)g.T;
     const unsigned long long vw = hw ? tw[nw] : 0ull, ve = he ? tw[ne] : 0ull;
     const unsigned long long vn = hn ? tw[nn] : 0ull, vs = hs ? tw[ns] : 0ull;
     unsigned long long *cw = (unsigned long long *)g.T;
@@ -235,6 +237,39 @@ ALI_DEV int ali_band_accept(const AliBandGrid &g, int iz, int ix, unsigned *nb)
 #endif
     return cnt;
 }
+
+#if defined(__CUDACC__)
+// ali_band_accept in two steps, so that the state words of the NEXT entry a thread will accept are in flight
+// while it claims for the current one (tiled fields only).  A word loaded early can only be stale as "far".
+ALI_DEV void ali_band_accept_peek(const AliBandGrid &g, int iz, int ix, unsigned long long &vw, unsigned long long &ve,
+                                  unsigned long long &vn, unsigned long long &vs)
+{
+    const size_t me = g.ti(iz, ix), trow = (size_t)g.t4x << 4;
+    const unsigned long long *tw = (const unsigned long long *)g.T;
+    vw = ix > 0 ? tw[(ix & 3) ? me - 1 : me - 13] : 0ull;
+    ve = ix < g.nx - 1 ? tw[((ix & 3) != 3) ? me + 1 : me + 13] : 0ull;
+    vn = iz > 0 ? tw[(iz & 3) ? me - 4 : me - trow + 12] : 0ull;
+    vs = iz < g.nz - 1 ? tw[((iz & 3) != 3) ? me + 4 : me + trow - 12] : 0ull;
+}
+
+ALI_DEV int ali_band_accept_peeked(const AliBandGrid &g, int iz, int ix, unsigned long long vw, unsigned long long ve,
+                                   unsigned long long vn, unsigned long long vs, unsigned *nb)
+{
+    int cnt = 0;
+    const size_t me = g.ti(iz, ix), trow = (size_t)g.t4x << 4;
+    g.st[me] = ALI_ST_ALIVE;
+    unsigned long long *cw = (unsigned long long *)g.T;
+    if (vw == ALI_T_FAR_BITS && atomicCAS(cw + ((ix & 3) ? me - 1 : me - 13), ALI_T_FAR_BITS, ALI_T_ENLISTED_BITS) == ALI_T_FAR_BITS)
+        nb[cnt++] = ALI_PACK(iz, ix - 1);
+    if (ve == ALI_T_FAR_BITS && atomicCAS(cw + (((ix & 3) != 3) ? me + 1 : me + 13), ALI_T_FAR_BITS, ALI_T_ENLISTED_BITS) == ALI_T_FAR_BITS)
+        nb[cnt++] = ALI_PACK(iz, ix + 1);
+    if (vn == ALI_T_FAR_BITS && atomicCAS(cw + ((iz & 3) ? me - 4 : me - trow + 12), ALI_T_FAR_BITS, ALI_T_ENLISTED_BITS) == ALI_T_FAR_BITS)
+        nb[cnt++] = ALI_PACK(iz - 1, ix);
+    if (vs == ALI_T_FAR_BITS && atomicCAS(cw + (((iz & 3) != 3) ? me + 4 : me + trow - 12), ALI_T_FAR_BITS, ALI_T_ENLISTED_BITS) == ALI_T_FAR_BITS)
+        nb[cnt++] = ALI_PACK(iz + 1, ix);
+    return cnt;
+}
+#endif
 
 // Largest phase velocity a coarse node can produce (1-degree sampling), for delta.
 ALI_DEV double ali_node_vmax(const AliModel &m, int iz, int ix)

@@ -412,17 +412,31 @@ __global__ void __launch_bounds__(NT) ali_march_kernel(AliBatch b, int smem_cap)
         const unsigned long long tminb = s_evalmin[cur] < s_basemin[cur] ? s_evalmin[cur] : s_basemin[cur];
         const double thr = __longlong_as_double((long long)tminb) + b.delta;
         double bmin = 1e300;
+        // software pipeline over a thread's entries: (entry, value) are loaded two passes ahead and the four
+        // neighbour state words of an entry that will be accepted one pass ahead, so that the L2 round trips of
+        // consecutive passes overlap instead of forming one chain
+        unsigned e1 = 0, e2 = 0;
+        double v1 = 0.0, v2 = 0.0;
+        unsigned long long sw = 0ull, se = 0ull, sn = 0ull, ss = 0ull;
+        if (tid < n) { e1 = ent[tid]; v1 = val[tid]; }
+        if (tid + NT < n) { e2 = ent[tid + NT]; v2 = val[tid + NT]; }
+        if (tid < n && !(v1 > thr)) ali_band_accept_peek(g, ALI_PACK_Z(e1), ALI_PACK_X(e1), sw, se, sn, ss);
         for (int base = 0; base < n; base += NT) {
             const int i = base + tid;
             int k = 0, kw = 0;
             unsigned out[4];
             double v = 0.0;
+            const unsigned e = e1;
+            const double v_mine = v1;
+            const unsigned long long cw_ = sw, ce_ = se, cn_ = sn, cs_ = ss;
+            e1 = e2; v1 = v2;
+            if (i + 2 * NT < n) { e2 = ent[i + 2 * NT]; v2 = val[i + 2 * NT]; }
+            if (i + NT < n && !(v1 > thr)) ali_band_accept_peek(g, ALI_PACK_Z(e1), ALI_PACK_X(e1), sw, se, sn, ss);
             if (i < n) {
-                const unsigned e = ent[i];
-                v = val[i];
+                v = v_mine;
                 const int iz = ALI_PACK_Z(e), ix = ALI_PACK_X(e);
                 if (!(v > thr)) {   // also a NaN value (degenerate material): the reference pops it too; never loops
-                    k = ali_band_accept(g, iz, ix, out); // new nodes: always evaluated next round
+                    k = ali_band_accept_peeked(g, iz, ix, cw_, ce_, cn_, cs_, out); // new nodes: always evaluated next round
                     kw = k;
                     v = 0.0;
                 } else {

@@ -1,0 +1,2 @@
+cd ${GRAFT_REPO_ROOT:-/root/repo}; mkdir -p gpurun_out
+ALIFMM_DEBUG=1 timeout 600 python tests/probes/gpu_probe.py --nsrc 128 --check 0 2>&1 | grep -v "^create" | cut -c1-400
