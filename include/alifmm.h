@@ -92,8 +92,9 @@ void alifmm_destroy(alifmm_ctx *ctx);
  * a multiple of nz+nx of the solved grid, default 6), "threads_per_source" (CTA size of
  * the band march: 256, 512, 640, 768, 896 or 1024; default 768 = 80 registers per thread, measured
  * fastest on B200), "cluster_size" (CTAs = SMs per source in the band march: 0 = automatic, the largest of
- * 8 / 4 / 2 / 1 that keeps every source of the batch resident at once; results do not depend on it),
- * "cluster_threads" (CTA size of the cluster march, 512 or 768), "seq_threads" (CTA size of the sequential
+ * 8 ... 1 that keeps every source of the batch resident at once -- 16 sources: 6, 32: 4, 64: 2; results do not depend on it),
+ * "cluster_threads" (CTA size of the cluster march, 512 or 768; 0 = automatic: 768 for pairs, else 512), "ray_min_blocks"
+ * (CTAs of four ray warps per SM the ray kernel is compiled for: 4 = 126 registers, the default; 5, 6 spill), "seq_threads" (CTA size of the sequential
  * near-source kernel: 32 = one warp per source, the default and measured fastest; 64, 128 or 256 evaluate one
  * speculated node per warp between two CTA barriers -- same result, ~8 % slower on B200), "band_smem_kb" (shared memory for the band lists, 0..180, default 0 = keep L1
  * for the field gathers), "resort_every" (re-order the band

@@ -417,7 +417,7 @@ def test_cluster_march_equals_single_cta(capi):
         A = ctx.ttf(iz, ix, sg)
         ca = ctx.counters()
         assert ca["cluster_size"] == 1
-        for cs, ct in ((2, 768), (4, 512), (8, 512), (8, 768), (0, 0)):
+        for cs, ct in ((2, 768), (2, 0), (3, 768), (4, 512), (5, 512), (6, 512), (7, 768), (8, 512), (8, 768), (0, 0)):
             ctx.set_option("cluster_size", cs)
             ctx.set_option("cluster_threads", ct)
             B = ctx.ttf(iz, ix, sg)
