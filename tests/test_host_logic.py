@@ -38,6 +38,8 @@ def test_no_gpu_means_loud_failure(built_library):
     fm = ALI_FMM(m["veln"], m["velpn"], m["vel_map"], m["scx"][:1] * 0.1, m["scz"][:1] * 0.1)
     with pytest.raises(_capi.AlifmmError):
         fm.update(m["veln"], m["velpn"], m["vel_map"])
+    with pytest.raises(_capi.AlifmmError):   # the two-GPU strip solve needs two devices, and says so
+        _capi.ttf_split(np.zeros((128, 16)), np.ones((128, 16), dtype=int), np.ones((128, 16)), None, True, g, g, 1e-3, 10, 5)
 
 
 def test_product_never_imports_the_oracle():
