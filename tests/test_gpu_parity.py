@@ -670,8 +670,13 @@ def test_two_gpu_strips_equal_one_gpu(capi):
         for (sz, sx), split in runs:
             one = ctx.ttf(np.array([sz], dtype=np.int32), np.array([sx], dtype=np.int32), 1)[0]
             c1 = ctx.counters()
-            two, c2 = capi.ttf_split(m["veln"], m["velpn"], m["vel_map"], m["stif_den"], True, g, p, m["dnx"], sz, sx,
-                                     devices=(0, 1), split_row=split)
+            try:
+                two, c2 = capi.ttf_split(m["veln"], m["velpn"], m["vel_map"], m["stif_den"], True, g, p, m["dnx"], sz, sx,
+                                         devices=(0, 1), split_row=split)
+            except capi.AlifmmError as e:
+                if "cannot access each other" in str(e):
+                    pytest.skip("the two devices are not peer-accessible")
+                raise
             assert np.array_equal(one, two), (m["veln"].shape, sz, sx, split, models.rel_err(one, two).max())
             # same rounds; never more evaluations (the window-change bitmap is folded 512 x 512, and a strip's bitmap
             # only receives its own marks and the boundary's: fewer aliases, so fewer value-preserving re-evaluations)
