@@ -130,8 +130,8 @@ def velocity_curves_batch(materials, device=0):
 
 
 def ttf_split(veln, velpn, vel_map, stif_den, has_stif, group_vel, phase_vel, dnx, src_iz, src_ix, devices=(0, 1), split_row=-1):
-    """One coarse field (travel(), subgrid 1) decomposed into two row strips on two GPUs (alifmm_ttf_split).
-    Returns (field float64 [nz, nx], counters dict)."""
+    """One coarse field (travel(), subgrid 1) decomposed into row strips on len(devices) = 2 ... 8 GPUs
+    (alifmm_ttf_split).  Returns (field float64 [nz, nx], counters dict)."""
     veln = np.ascontiguousarray(veln, dtype=np.float64)
     velpn = np.ascontiguousarray(velpn, dtype=np.int32)
     vel_map = np.ascontiguousarray(vel_map, dtype=np.float64)

@@ -1,4 +1,4 @@
-// ali_strip.cuh -- one travel-time field decomposed into two row strips on two GPUs (BASELINE config 5).
+// ali_strip.cuh -- one travel-time field decomposed into row strips on 2 ... 8 GPUs (BASELINE config 5).
 //
 // The reference has no counterpart (a single field is one heap, ATR:2055-2102); SURVEY.md 8(e) asks for row
 // strips with a 2-row halo (the stencil reaches two nodes, ATR:940-987) exchanged over NVLink and a scalar
@@ -18,45 +18,54 @@
 //     peer's exchange block;
 //   * the three barriers of a round become: cluster barrier, system fence, epoch flag stored to the peer and
 //     awaited from the peer, cluster barrier.
+// With more than two strips a GPU has a peer above and a peer below for the halo traffic, and the scalars of a round
+// (minimum, band length, flags, barrier epoch) go to EVERY other GPU's exchange block, one slot per writer.
 // The set of nodes evaluated, published, accepted and enlisted per round is that of the one-GPU kernel, so the
-// field is bit-identical to it (tests/test_gpu_parity.py::test_two_gpu_strips_equal_one_gpu).
+// field is bit-identical to it (tests/test_gpu_parity.py::test_two_gpu_strips_equal_one_gpu, ..._four_...).
 #pragma once
 
-struct AliStripXchg {                 // written by the PEER over NVLink, read locally with volatile loads
+#define ALI_MAX_STRIPS 8
+
+struct AliStripXchg {                 // slot w of a GPU's exchange block: written by strip w over NVLink, read locally
     unsigned long long flag;          // inter-GPU barrier epoch
-    unsigned long long evalmin[2], basemin[2];   // the peer's minima, by round parity
-    int count[2];                     // the peer's band length at the start of the round, by round parity
+    unsigned long long evalmin[2], basemin[2];   // the writer's minima, by round parity
+    int count[2];                     // the writer's band length at the start of the round, by round parity
     int force[2];
     int overflow, pad;
 };
 
-struct AliStripArgs {
-    AliBatch b;                 // nz / nx: the FULL grid; Tt, st and the model records are offset to full-grid indexing
-    AliClusterCtl *ctl;         // local control block (also written by the peer: list counters, bitmap)
-    AliStripXchg *xl;           // local exchange block (written by the peer)
-    int zlo, zhi;               // rows this GPU owns
-    int has_seq;                // this GPU ran the sequential near-source phase (it owns the source)
-    double *pT;                 // the peer's field / alive flags / control block / exchange block / lists
-    uint8_t *pst;
-    AliClusterCtl *pctl;
-    AliStripXchg *px;
-    unsigned *plists;           // ent0 | ent1 | wrk0 | wrk1, band_cap entries each
-    double *pstage;             // val0 | val1
-    long long spin_limit;       // iterations a GPU waits for its peer before giving up (overflow code 4)
+struct AliStripPeer {           // the strip above (index 0) / below (index 1): field, alive flags, control block, lists
+    double *T;
+    uint8_t *st;
+    AliClusterCtl *ctl;
+    unsigned *lists;            // ent0 | ent1 | wrk0 | wrk1, band_cap entries each
+    double *stage;              // val0 | val1
 };
 
-// Inter-GPU barrier.  Every thread fences its remote stores at system scope, the cluster meets, thread 0
-// announces the epoch to the peer and waits for the peer's, the cluster meets again (its acquire side also
-// invalidates L1, so plain loads see what the peer stored into local memory).
+struct AliStripArgs {
+    AliBatch b;                 // nz / nx: the FULL grid; Tt, st and the model records are offset to full-grid indexing
+    AliClusterCtl *ctl;         // local control block (also written by the neighbours: list counters, bitmap)
+    AliStripXchg *xl;           // local exchange block: ALI_MAX_STRIPS slots, slot w written by strip w
+    int n_strips, me;
+    int zlo, zhi;               // rows this GPU owns
+    int has_seq;                // this GPU ran the sequential near-source phase (it owns the source)
+    AliStripPeer nb[2];         // above (rows < zlo), below (rows >= zhi); null pointers at the ends of the chain
+    AliStripXchg *px[ALI_MAX_STRIPS];   // every strip's exchange block (px[me] == xl)
+    long long spin_limit;       // iterations a GPU waits for a peer before giving up (overflow code 4)
+};
+
+// Inter-GPU barrier.  Every thread fences its remote stores at system scope, the cluster meets, thread w (w < n_strips,
+// w != me) announces the epoch to strip w and waits for strip w's, the cluster meets again (its acquire side also
+// invalidates L1, so plain loads see what the peers stored into local memory).
 __device__ __forceinline__ bool ali_strip_sync(const AliStripArgs &a, unsigned long long &epoch, int gtid)
 {
     __threadfence_system();
     ali_cluster_sync();
     epoch++;
-    if (gtid == 0) {
-        *(volatile unsigned long long *)&a.px->flag = epoch;
+    if (gtid < a.n_strips && gtid != a.me) {
+        *(volatile unsigned long long *)&a.px[gtid][a.me].flag = epoch;
         long long spins = 0;
-        while (*(volatile unsigned long long *)&a.xl->flag < epoch) {
+        while (*(volatile unsigned long long *)&a.xl[gtid].flag < epoch) {
             if (++spins > a.spin_limit) { a.ctl->overflow = 4; break; }
             __nanosleep(64);
         }
@@ -91,9 +100,7 @@ __global__ void __launch_bounds__(NT) ali_march_strip_kernel(AliStripArgs a)
     const int cap = b.band_cap;
     double *val0 = b.stage, *val1 = val0 + cap;
     unsigned *ent0 = b.lists, *ent1 = ent0 + cap, *wrk0 = ent1 + cap, *wrk1 = wrk0 + cap;
-    double *pval0 = a.pstage, *pval1 = pval0 + cap;
-    unsigned *pent0 = a.plists, *pent1 = pent0 + cap, *pwrk0 = pent1 + cap, *pwrk1 = pwrk0 + cap;
-    const bool peer_above = a.zlo > 0, peer_below = a.zhi < b.nz;
+    const bool peer_above = a.me > 0, peer_below = a.me < a.n_strips - 1;
 
     for (int q = tid; q < ALI_MT_WORDS; q += NT) s_sincos[q] = q < ALI_GL_SINCOSTAB_COUNT ? ali_gl_sincostab[q] : ali_gl_atan_cij[q - ALI_GL_SINCOSTAB_COUNT];
     if (tid == 0) { s_grid = g; s_evals = 0; s_fbs = 0; }
@@ -143,8 +150,6 @@ __global__ void __launch_bounds__(NT) ali_march_strip_kernel(AliStripArgs a)
         double *val = cur == 0 ? val0 : val1, *nval = cur == 0 ? val1 : val0;
         unsigned *ent = cur == 0 ? ent0 : ent1, *nent = cur == 0 ? ent1 : ent0;
         unsigned *wrk = cur == 0 ? wrk0 : wrk1, *nwrk = cur == 0 ? wrk1 : wrk0;
-        double *pnval = cur == 0 ? pval1 : pval0;
-        unsigned *pnent = cur == 0 ? pent1 : pent0, *pnwrk = cur == 0 ? pwrk1 : pwrk0;
         rounds++;
         const int par = rounds & 1;
         if (n > max_band) max_band = n;
@@ -183,23 +188,22 @@ __global__ void __launch_bounds__(NT) ali_march_strip_kernel(AliStripArgs a)
             atomicMin(&ctl->evalmin[cur], (unsigned long long)__double_as_longlong(lmin));
         if (!(alive = ali_strip_sync(a, epoch, gtid))) break;
         // ---- phase B: publish (also into the peer's halo rows), mark, tell the peer this strip's minimum and length
-        if (gtid == 0) {
-            ctl->force[(rounds + 1) & 1] = 0;
-            a.px->evalmin[par] = ali_ldv(&ctl->evalmin[cur]);
-            a.px->basemin[par] = ali_ldv(&ctl->basemin[cur]);
-            a.px->count[par] = n;
-            a.px->force[par] = ali_ldv(&ctl->force[par]);
-            a.px->overflow = ali_ldv(&ctl->overflow);
+        if (gtid == 0) ctl->force[(rounds + 1) & 1] = 0;
+        if (gtid < a.n_strips && gtid != a.me) {
+            AliStripXchg *x = &a.px[gtid][a.me];
+            x->evalmin[par] = ali_ldv(&ctl->evalmin[cur]);
+            x->basemin[par] = ali_ldv(&ctl->basemin[cur]);
+            x->count[par] = n;
+            x->force[par] = ali_ldv(&ctl->force[par]);
+            x->overflow = ali_ldv(&ctl->overflow);
         }
         auto publish = [&](unsigned e, double v) {
             const int z = ALI_PACK_Z(e), x = ALI_PACK_X(e);
             const size_t node = g.ti(z, x);
             g.T[node] = v;
             ali_dmap_mark(ctl->dmap, z, x);
-            if ((peer_above && z < a.zlo + 2) || (peer_below && z >= a.zhi - 2)) {
-                a.pT[node] = v;
-                ali_dmap_mark(a.pctl->dmap, z, x);
-            }
+            if (peer_above && z < a.zlo + 2) { a.nb[0].T[node] = v; ali_dmap_mark(a.nb[0].ctl->dmap, z, x); }
+            if (peer_below && z >= a.zhi - 2) { a.nb[1].T[node] = v; ali_dmap_mark(a.nb[1].ctl->dmap, z, x); }
         };
         if (pmask & 1) publish(pe0, pv0);
         if (pmask & 2) publish(pe1, pv1);
@@ -214,14 +218,19 @@ __global__ void __launch_bounds__(NT) ali_march_strip_kernel(AliStripArgs a)
         if (!(alive = ali_strip_sync(a, epoch, gtid))) break;
         // ---- phase C: accept against the minimum of BOTH strips; neighbours across the boundary are claimed from,
         // and appended to, the peer
-        const int total = n + *(volatile int *)&a.xl->count[par];
-        const int ovf = ali_ldv(&ctl->overflow) | *(volatile int *)&a.xl->overflow;
-        if (total == 0 || ovf) { if (total == 0) rounds--; break; }   // (the round that finds both lists empty did no work)
-        const int force = ali_ldv(&ctl->force[par]) | *(volatile int *)&a.xl->force[par];
+        int total = n, ovf = ali_ldv(&ctl->overflow), force = ali_ldv(&ctl->force[par]);
         unsigned long long tm = ali_ldv(&ctl->evalmin[cur]);
-        { const unsigned long long o1 = ali_ldv(&ctl->basemin[cur]), o2 = *(volatile unsigned long long *)&a.xl->evalmin[par],
-                                   o3 = *(volatile unsigned long long *)&a.xl->basemin[par];
-          tm = tm < o1 ? tm : o1; tm = tm < o2 ? tm : o2; tm = tm < o3 ? tm : o3; }
+        { const unsigned long long o1 = ali_ldv(&ctl->basemin[cur]); tm = tm < o1 ? tm : o1; }
+        for (int w = 0; w < a.n_strips; w++) {
+            if (w == a.me) continue;
+            const AliStripXchg *x = &a.xl[w];
+            total += *(volatile const int *)&x->count[par];
+            ovf |= *(volatile const int *)&x->overflow;
+            force |= *(volatile const int *)&x->force[par];
+            const unsigned long long o2 = *(volatile const unsigned long long *)&x->evalmin[par], o3 = *(volatile const unsigned long long *)&x->basemin[par];
+            tm = tm < o2 ? tm : o2; tm = tm < o3 ? tm : o3;
+        }
+        if (total == 0 || ovf) { if (total == 0) rounds--; break; }   // (the round that finds every list empty did no work)
         const double thr = __longlong_as_double((long long)tm) + b.delta;
         double bmin = 1e300;
         for (int i = q0; i - (tid & 31) < n; i += GT) {
@@ -235,8 +244,9 @@ __global__ void __launch_bounds__(NT) ali_march_strip_kernel(AliStripArgs a)
                 if (!(v > thr)) {
                     const size_t me = g.ti(iz, ix);
                     g.st[me] = ALI_ST_ALIVE;
-                    if ((peer_above && iz < a.zlo + 2) || (peer_below && iz >= a.zhi - 2)) a.pst[me] = ALI_ST_ALIVE;
-                    unsigned long long *cw = (unsigned long long *)g.T, *pw = (unsigned long long *)a.pT;
+                    if (peer_above && iz < a.zlo + 2) a.nb[0].st[me] = ALI_ST_ALIVE;
+                    if (peer_below && iz >= a.zhi - 2) a.nb[1].st[me] = ALI_ST_ALIVE;
+                    unsigned long long *cw = (unsigned long long *)g.T;
                     const volatile unsigned long long *tw = (const volatile unsigned long long *)g.T;
 #pragma unroll
                     for (int dir = 0; dir < 4; dir++) {
@@ -246,17 +256,23 @@ __global__ void __launch_bounds__(NT) ali_march_strip_kernel(AliStripArgs a)
                         if (z >= a.zlo && z < a.zhi) {
                             if (tw[nb] == ALI_T_FAR_BITS && atomicCAS(cw + nb, ALI_T_FAR_BITS, ALI_T_ENLISTED_BITS) == ALI_T_FAR_BITS)
                                 out[k++] = ALI_PACK(z, x);
-                        } else if (atomicCAS(pw + nb, ALI_T_FAR_BITS, ALI_T_ENLISTED_BITS) == ALI_T_FAR_BITS) {
-                            // the peer owns it: into the peer's next list, as a new node (evaluated next round)
-                            const int pos = atomicAdd(&a.pctl->count[cur ^ 1], 1);
-                            if (pos < cap) {
-                                const int wpos = atomicAdd(&a.pctl->nwork[cur ^ 1], 1);
-                                pnent[pos] = ALI_PACK(z, x);
-                                pnval[pos] = 0.0;
-                                pnwrk[wpos] = (unsigned)pos;
-                            } else {
-                                a.pctl->overflow = 2;
-                                ctl->overflow = 2;
+                        } else {
+                            const AliStripPeer &pr = a.nb[z < a.zlo ? 0 : 1];
+                            if (atomicCAS((unsigned long long *)pr.T + nb, ALI_T_FAR_BITS, ALI_T_ENLISTED_BITS) == ALI_T_FAR_BITS) {
+                                // the neighbour owns it: into ITS next list, as a new node (evaluated next round)
+                                const int pos = atomicAdd(&pr.ctl->count[cur ^ 1], 1);
+                                if (pos < cap) {
+                                    const int wpos = atomicAdd(&pr.ctl->nwork[cur ^ 1], 1);
+                                    unsigned *pl = pr.lists + (cur == 0 ? cap : 0);            // its next entry list
+                                    unsigned *pw = pr.lists + 2 * cap + (cur == 0 ? cap : 0);  // its next work list
+                                    double *pv = pr.stage + (cur == 0 ? cap : 0);
+                                    pl[pos] = ALI_PACK(z, x);
+                                    pv[pos] = 0.0;
+                                    pw[wpos] = (unsigned)pos;
+                                } else {
+                                    pr.ctl->overflow = 2;
+                                    ctl->overflow = 2;
+                                }
                             }
                         }
                     }
@@ -372,7 +388,9 @@ __global__ void __launch_bounds__(NT) ali_march_strip_kernel(AliStripArgs a)
         if (rank == 0) {
             rec.rounds = rounds;
             rec.max_band = max_band;
-            const int ovf = ali_ldv(&ctl->overflow) | *(volatile int *)&a.xl->overflow;
+            int ovf = ali_ldv(&ctl->overflow);
+            for (int w = 0; w < a.n_strips; w++)
+                if (w != a.me) ovf |= *(volatile const int *)&a.xl[w].overflow;
             if (ovf) rec.overflow = ovf;
         }
     }

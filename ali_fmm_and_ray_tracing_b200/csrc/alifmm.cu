@@ -2165,31 +2165,45 @@ extern "C" int alifmm_ttf_split(const alifmm_model_desc *d, int32_t n_dev, const
                                 int32_t src_ix, int32_t split_row, double *out_host, alifmm_counters_t *counters)
 {
     if (!d || !devices || !out_host) return fail(ALIFMM_E_INVALID, "alifmm_ttf_split: null argument");
-    if (n_dev != 2) return fail(ALIFMM_E_INVALID, "alifmm_ttf_split: exactly two devices (row strips with one boundary)");
+    if (n_dev < 2 || n_dev > ALI_MAX_STRIPS) return fail(ALIFMM_E_INVALID, "alifmm_ttf_split: 2 ... 8 devices (a chain of row strips)");
     if (d->nz < 64 || d->nx < 1 || !(d->dnx > 0) || !d->veln || !d->velpn || !d->vel_map || !d->group_vel || !d->phase_vel || d->n_cols < 1)
         return fail(ALIFMM_E_INVALID, "alifmm_ttf_split: bad model descriptor (at least 64 rows)");
     if (d->nz > 65535 || d->nx > 65535) return fail(ALIFMM_E_INVALID, "alifmm_ttf_split: grid side exceeds 65535 nodes");
     if (src_iz < 0 || src_iz >= d->nz || src_ix < 0 || src_ix >= d->nx) return fail(ALIFMM_E_INVALID, "alifmm_ttf_split: source node outside the grid");
-    if (devices[0] == devices[1]) return fail(ALIFMM_E_INVALID, "alifmm_ttf_split: two different devices");
+    if (split_row > 0 && n_dev != 2) return fail(ALIFMM_E_INVALID, "alifmm_ttf_split: an explicit split row only with two devices");
     int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 2) { cudaGetLastError(); return fail(ALIFMM_E_CUDA, "alifmm_ttf_split: needs two CUDA devices"); }
-    for (int k = 0; k < 2; k++)
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < n_dev) { cudaGetLastError(); return fail(ALIFMM_E_CUDA, "alifmm_ttf_split: needs as many CUDA devices as strips"); }
+    for (int k = 0; k < n_dev; k++) {
         if (devices[k] < 0 || devices[k] >= ndev) return fail(ALIFMM_E_INVALID, "alifmm_ttf_split: device index out of range");
+        for (int j = 0; j < k; j++)
+            if (devices[j] == devices[k]) return fail(ALIFMM_E_INVALID, "alifmm_ttf_split: the devices must differ");
+    }
     const int nz = d->nz, nx = d->nx, margin = 27;
     AliSourcePlan plan;
     AliModel pm{}; pm.nz = nz; pm.nx = nx;
     ali_make_plan(plan, pm, src_iz, src_ix, 1, margin);
     const int keep = plan.stop_r + 8;   // the sequential phase's window (stop_r + 4 each way) must lie inside one strip
-    int zs = split_row > 0 ? split_row : nz / 2;
-    zs &= ~3;
-    if (split_row <= 0 && abs(zs - src_iz) < keep) zs = (src_iz + keep + 3) & ~3;
-    if (split_row <= 0 && zs > nz - 8) zs = (src_iz - keep) & ~3;
-    if (zs < 8 || zs > nz - 8 || (zs > src_iz ? zs - src_iz : src_iz - zs + 1) < keep)
-        return fail(ALIFMM_E_INVALID, "alifmm_ttf_split: no admissible split row (the source's refined neighbourhood must lie inside one strip)");
+    // strip k owns rows [zb[k], zb[k + 1]): equal shares, boundaries on multiples of 4 (tile rows), the boundaries next
+    // to the source pushed away from it
+    int zb[ALI_MAX_STRIPS + 1];
+    zb[0] = 0; zb[n_dev] = nz;
+    for (int k = 1; k < n_dev; k++) zb[k] = (int)((long long)nz * k / n_dev) & ~3;
+    if (split_row > 0) zb[1] = split_row & ~3;
+    else
+        for (int k = 1; k < n_dev; k++) {
+            if (zb[k] <= src_iz && src_iz - zb[k] + 1 < keep) zb[k] = (src_iz - keep) & ~3;         // boundary above the source: up
+            else if (zb[k] > src_iz && zb[k] - src_iz < keep) zb[k] = (src_iz + keep + 3) & ~3;      // below: down
+        }
+    for (int k = 1; k < n_dev; k++) {
+        const bool near = zb[k] <= src_iz ? (src_iz - zb[k] + 1 < keep) : (zb[k] - src_iz < keep);
+        if (zb[k] < 8 || zb[k] > nz - 8 || zb[k] - zb[k - 1] < 16 || near)
+            return fail(ALIFMM_E_INVALID, "alifmm_ttf_split: no admissible split rows (strips of at least 16 rows, the source's refined neighbourhood inside one strip)");
+    }
+    if (nz - zb[n_dev - 1] < 8) return fail(ALIFMM_E_INVALID, "alifmm_ttf_split: no admissible split rows");
     for (size_t i = 0; i < (size_t)nz * nx; i++)
         if (d->velpn[i] < 0 || d->velpn[i] >= d->n_cols) return fail(ALIFMM_E_INVALID, "alifmm_ttf_split: velpn holds a material id outside the velocity tables");
 
-    StripDev S[2];
+    StripDev S[ALI_MAX_STRIPS];
     int rc = ALIFMM_OK;
     std::string err;
     auto cleanup = [&]() {
@@ -2207,7 +2221,9 @@ extern "C" int alifmm_ttf_split(const alifmm_model_desc *d, int32_t n_dev, const
     } while (0)
     const size_t t4x = (size_t)((nx + 3) >> 2);
     const int band_cap = (int)(6.0 * (double)(nz + nx)) + 1024;
-    const int owner = src_iz < zs ? 0 : 1;
+    int owner = 0;
+    for (int k = 0; k < n_dev; k++)
+        if (src_iz >= zb[k] && src_iz < zb[k + 1]) owner = k;
     size_t seq_cap = 0; int heap_cap = 0;
     {
         size_t lvl = ali_plan_max_level_nodes(plan);
@@ -2215,18 +2231,21 @@ extern "C" int alifmm_ttf_split(const alifmm_model_desc *d, int32_t n_dev, const
         seq_cap = lvl > w * w ? lvl : w * w;
         heap_cap = (int)(seq_cap / 2 + 64);
     }
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < n_dev; k++) {
         StripDev &s = S[k];
         s.device = devices[k];
-        s.zlo = k == 0 ? 0 : zs; s.zhi = k == 0 ? zs : nz;
-        s.za = k == 0 ? 0 : zs - 4; s.zb = k == 0 ? zs + 4 : ((nz + 3) & ~3);
+        s.zlo = zb[k]; s.zhi = zb[k + 1];
+        s.za = k == 0 ? 0 : s.zlo - 4; s.zb = k == n_dev - 1 ? ((nz + 3) & ~3) : s.zhi + 4;
         STRIP_TRY(cudaSetDevice(s.device));
-        int can = 0;
-        STRIP_TRY(cudaDeviceCanAccessPeer(&can, s.device, devices[k ^ 1]));
-        if (!can) { cleanup(); return fail(ALIFMM_E_CUDA, "alifmm_ttf_split: the two devices cannot access each other's memory"); }
-        cudaError_t pe = cudaDeviceEnablePeerAccess(devices[k ^ 1], 0);
-        if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) STRIP_TRY(pe);
-        cudaGetLastError();
+        for (int j = 0; j < n_dev; j++) {
+            if (j == k) continue;
+            int can = 0;
+            STRIP_TRY(cudaDeviceCanAccessPeer(&can, s.device, devices[j]));
+            if (!can) { cleanup(); return fail(ALIFMM_E_CUDA, "alifmm_ttf_split: the devices cannot access each other's memory"); }
+            cudaError_t pe = cudaDeviceEnablePeerAccess(devices[j], 0);
+            if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) STRIP_TRY(pe);
+            cudaGetLastError();
+        }
         STRIP_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         auto alloc = [&](size_t bytes, void **out) -> cudaError_t {
             cudaError_t e = cudaMalloc(out, bytes < 256 ? 256 : bytes);
@@ -2279,12 +2298,12 @@ extern "C" int alifmm_ttf_split(const alifmm_model_desc *d, int32_t n_dev, const
         STRIP_TRY(alloc(tn * 8, (void **)&s.Tt)); STRIP_TRY(alloc(tn + 16, (void **)&s.st));
         STRIP_TRY(alloc((size_t)(s.zhi - s.zlo) * nx * 8, (void **)&s.out));
         STRIP_TRY(alloc((size_t)4 * band_cap * 4, (void **)&s.lists)); STRIP_TRY(alloc((size_t)2 * band_cap * 8, (void **)&s.stage));
-        STRIP_TRY(alloc(sizeof(AliClusterCtl), (void **)&s.ctl)); STRIP_TRY(alloc(sizeof(AliStripXchg), (void **)&s.xchg));
+        STRIP_TRY(alloc(sizeof(AliClusterCtl), (void **)&s.ctl)); STRIP_TRY(alloc(ALI_MAX_STRIPS * sizeof(AliStripXchg), (void **)&s.xchg));
         STRIP_TRY(alloc(sizeof(AliSourceRec), (void **)&s.rec));
         STRIP_TRY(cudaMemsetAsync(s.Tt, ALI_T_UNSET_BYTE, tn * 8, s.stream));
         STRIP_TRY(cudaMemsetAsync(s.st, 0, tn + 16, s.stream));
         STRIP_TRY(cudaMemsetAsync(s.ctl, 0, sizeof(AliClusterCtl), s.stream));
-        STRIP_TRY(cudaMemsetAsync(s.xchg, 0, sizeof(AliStripXchg), s.stream));
+        STRIP_TRY(cudaMemsetAsync(s.xchg, 0, ALI_MAX_STRIPS * sizeof(AliStripXchg), s.stream));
         AliSourceRec hr;
         memset(&hr, 0, sizeof hr);
         hr.src_iz = src_iz; hr.src_ix = src_ix;
@@ -2296,11 +2315,13 @@ extern "C" int alifmm_ttf_split(const alifmm_model_desc *d, int32_t n_dev, const
         }
         STRIP_TRY(cudaStreamSynchronize(s.stream));
     }
-    const double vmax = S[0].vmax > S[1].vmax ? S[0].vmax : S[1].vmax;
+    double vmax = 0.0;
+    for (int k = 0; k < n_dev; k++) vmax = S[k].vmax > vmax ? S[k].vmax : vmax;
     if (!(vmax > 0) || !isfinite(vmax)) { cleanup(); return fail(ALIFMM_E_INVALID, "alifmm_ttf_split: model has no positive finite phase velocity"); }
-    AliStripArgs A[2];
-    for (int k = 0; k < 2; k++) {
+    AliStripArgs A[ALI_MAX_STRIPS];
+    for (int k = 0; k < n_dev; k++) {
         StripDev &s = S[k];
+        memset(&A[k], 0, sizeof A[k]);
         AliBatch &b = A[k].b;
         memset(&b, 0, sizeof b);
         b.m = s.m; b.m_dev = s.m_dev; b.sg = 1; b.nz = nz; b.nx = nx; b.margin = margin;
@@ -2312,13 +2333,19 @@ extern "C" int alifmm_ttf_split(const alifmm_model_desc *d, int32_t n_dev, const
         b.seq_cap = seq_cap; b.heap_cap = heap_cap;
         b.lists = s.lists; b.stage = s.stage; b.band_cap = band_cap; b.resort_every = 8; b.rec = s.rec;
         A[k].ctl = s.ctl; A[k].xl = s.xchg; A[k].zlo = s.zlo; A[k].zhi = s.zhi; A[k].has_seq = k == owner;
+        A[k].n_strips = n_dev; A[k].me = k;
         A[k].spin_limit = 400000000LL;   // ~ a minute of 64 ns sleeps: a dead peer ends the kernel instead of hanging the GPU
     }
-    for (int k = 0; k < 2; k++) {
-        const StripDev &p = S[k ^ 1];
-        A[k].pT = p.Tt - (size_t)(p.za >> 2) * t4x * 16;
-        A[k].pst = p.st - (size_t)(p.za >> 2) * t4x * 16;
-        A[k].pctl = p.ctl; A[k].px = p.xchg; A[k].plists = p.lists; A[k].pstage = p.stage;
+    for (int k = 0; k < n_dev; k++) {
+        for (int j = 0; j < n_dev; j++) A[k].px[j] = S[j].xchg;
+        for (int side = 0; side < 2; side++) {
+            const int j = side == 0 ? k - 1 : k + 1;
+            if (j < 0 || j >= n_dev) continue;
+            const StripDev &p = S[j];
+            A[k].nb[side].T = p.Tt - (size_t)(p.za >> 2) * t4x * 16;
+            A[k].nb[side].st = p.st - (size_t)(p.za >> 2) * t4x * 16;
+            A[k].nb[side].ctl = p.ctl; A[k].nb[side].lists = p.lists; A[k].nb[side].stage = p.stage;
+        }
     }
     cudaEvent_t ev[3];
     STRIP_TRY(cudaSetDevice(S[owner].device));
@@ -2328,7 +2355,7 @@ extern "C" int alifmm_ttf_split(const alifmm_model_desc *d, int32_t n_dev, const
     STRIP_TRY(cudaGetLastError());
     STRIP_TRY(cudaEventRecord(ev[1], S[owner].stream));
     STRIP_TRY(cudaStreamSynchronize(S[owner].stream));
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < n_dev; k++) {
         STRIP_TRY(cudaSetDevice(S[k].device));
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(8); cfg.blockDim = dim3(512);
@@ -2339,8 +2366,8 @@ extern "C" int alifmm_ttf_split(const alifmm_model_desc *d, int32_t n_dev, const
         cfg.attrs = at; cfg.numAttrs = 1;
         STRIP_TRY(cudaLaunchKernelEx(&cfg, ali_march_strip_kernel<512>, A[k]));
     }
-    AliSourceRec recs[2];
-    for (int k = 0; k < 2; k++) {
+    AliSourceRec recs[ALI_MAX_STRIPS];
+    for (int k = 0; k < n_dev; k++) {
         STRIP_TRY(cudaSetDevice(S[k].device));
         if (k == owner) STRIP_TRY(cudaEventRecord(ev[2], S[k].stream));
         const size_t total = (size_t)(S[k].zhi - S[k].zlo) * nx;
@@ -2349,18 +2376,19 @@ extern "C" int alifmm_ttf_split(const alifmm_model_desc *d, int32_t n_dev, const
         ali_finalize_rows_kernel<<<blocks, 256, 0, S[k].stream>>>(A[k].b.Tt, A[k].b.st, S[k].out, S[k].zlo, S[k].zhi, nx);
         STRIP_TRY(cudaMemcpyAsync(&recs[k], S[k].rec, sizeof(AliSourceRec), cudaMemcpyDeviceToHost, S[k].stream));
     }
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < n_dev; k++) {
         STRIP_TRY(cudaSetDevice(S[k].device));
         STRIP_TRY(cudaStreamSynchronize(S[k].stream));
     }
-    const int ovf = recs[0].overflow | recs[1].overflow;
+    int ovf = 0;
+    for (int k = 0; k < n_dev; k++) ovf |= recs[k].overflow;
     if (ovf) {
         cleanup();
         if (ovf & 4) return fail(ALIFMM_E_CUDA, "alifmm_ttf_split: a GPU stopped answering the per-round exchange");
         if (ovf & 2) return fail(ALIFMM_E_CAPACITY, "alifmm_ttf_split: narrow-band list overflowed");
         return fail(ALIFMM_E_CAPACITY, "alifmm_ttf_split: sequential near-source scratch overflowed");
     }
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < n_dev; k++) {
         STRIP_TRY(cudaSetDevice(S[k].device));
         STRIP_TRY(cudaMemcpy(out_host + (size_t)S[k].zlo * nx, S[k].out, (size_t)(S[k].zhi - S[k].zlo) * nx * 8, cudaMemcpyDeviceToHost));
     }
@@ -2373,10 +2401,13 @@ extern "C" int alifmm_ttf_split(const alifmm_model_desc *d, int32_t n_dev, const
         counters->node_solves = (int64_t)nz * nx;
         counters->seq_pops = recs[owner].seq.cnt.pops; counters->seq_evals = recs[owner].seq.cnt.evals;
         counters->band_rounds = counters->band_rounds_max = recs[0].rounds;
-        counters->band_evals = recs[0].band_evals + recs[1].band_evals;
-        counters->fallback_evals = recs[owner].seq.cnt.fallbacks + recs[0].band_fallbacks + recs[1].band_fallbacks;
-        counters->max_band = recs[0].max_band + recs[1].max_band;
-        counters->kernel_launches = 5;
+        for (int k = 0; k < n_dev; k++) {
+            counters->band_evals += recs[k].band_evals;
+            counters->fallback_evals += recs[k].band_fallbacks;
+            counters->max_band += recs[k].max_band;
+        }
+        counters->fallback_evals += recs[owner].seq.cnt.fallbacks;
+        counters->kernel_launches = 1 + 2 * n_dev;
         counters->vmax = vmax; counters->delta = 0.35 * d->dnx / vmax;
         counters->cluster_size = 8; counters->seq_threads = 32;
     }

@@ -180,13 +180,15 @@ int alifmm_eval_nodes(int device, int32_t n, int32_t nz, int32_t nx, double dnx,
                       const int32_t *nsts, const int32_t *pos, double *out_update, double *out_fouds,
                       int32_t *out_stencil);
 
-/* One travel-time field (travel(), ATR:1463; subgrid 1) decomposed into two row strips on two GPUs: each device
- * holds its strip of the model and of the field plus a 2-row halo (the stencil reaches two nodes, ATR:940-987);
- * values published next to the boundary, claims of nodes across it and the per-round minimum / termination go
- * through peer-mapped memory over NVLink (no NCCL on the data path).  The reference has no counterpart (one
- * field is one heap); the result is bit-identical to alifmm_ttf() on one device.  The value is capacity, not
- * speed.  devices: two distinct, peer-accessible devices; split_row <= 0: automatic (near nz / 2, a multiple of
- * 4, keeping the source's refined neighbourhood inside one strip); out_host [nz * nx]; counters may be NULL. */
+/* One travel-time field (travel(), ATR:1463; subgrid 1) decomposed into row strips on 2 ... 8 GPUs (BASELINE config 5): each
+ * device holds its strip of the model and of the field plus a halo of one tile row either side (the stencil reaches two
+ * nodes, ATR:940-987); values published next to a boundary and claims of nodes across it go to the neighbouring strip,
+ * the per-round minimum / band length / termination to every strip, all through peer-mapped memory over NVLink (no NCCL
+ * on the data path).  The reference has no counterpart (one field is one heap); the result is bit-identical to alifmm_ttf()
+ * on one device.  The value is capacity, not speed.  devices: n_dev distinct, mutually peer-accessible devices, strip k
+ * (rows from the top) on devices[k]; split_row <= 0: automatic (equal shares, boundaries on multiples of 4, kept away
+ * from the source so that its refined neighbourhood lies inside one strip), > 0 only with two devices; out_host
+ * [nz * nx]; counters may be NULL. */
 int alifmm_ttf_split(const alifmm_model_desc *desc, int32_t n_dev, const int32_t *devices, int32_t src_iz, int32_t src_ix,
                      int32_t split_row, double *out_host, alifmm_counters_t *counters);
 

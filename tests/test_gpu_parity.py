@@ -689,6 +689,33 @@ def test_two_gpu_strips_equal_one_gpu(capi):
         capi.ttf_split(m["veln"], m["velpn"], m["vel_map"], m["stif_den"], True, g, p, m["dnx"], 384, 384, split_row=380)
 
 
+def test_four_and_eight_gpu_strips_equal_one_gpu(capi):
+    """The same decomposition as a chain of 4 (and, where the box has them, 8) strips: halo traffic to the strip above
+    and below, the round's scalars to every strip.  Bit-equal to one GPU, same number of rounds."""
+    n_gpu = capi.device_count()
+    if n_gpu < 4:
+        pytest.skip("needs four CUDA devices")
+    m = models.voronoi(1536, 300, 78)
+    g, p = _tables(m)
+    ctx = _ctx(capi, m)
+    for n_strips in (4, 8):
+        if n_gpu < n_strips:
+            continue
+        for sz, sx in ((100, 700), (800, 50), (1535, 1535), (385, 768)):   # (the last one sits next to an even boundary)
+            one = ctx.ttf(np.array([sz], dtype=np.int32), np.array([sx], dtype=np.int32), 1)[0]
+            c1 = ctx.counters()
+            try:
+                two, c2 = capi.ttf_split(m["veln"], m["velpn"], m["vel_map"], m["stif_den"], True, g, p, m["dnx"], sz, sx,
+                                         devices=tuple(range(n_strips)))
+            except capi.AlifmmError as e:
+                if "cannot access each other" in str(e):
+                    pytest.skip("the devices are not peer-accessible")
+                raise
+            assert np.array_equal(one, two), (n_strips, sz, sx, models.rel_err(one, two).max())
+            assert c2["band_rounds"] == c1["band_rounds"], (c1, c2)
+    ctx.close()
+
+
 # ----------------------------------------------------------------------------- reference-facing API
 def test_class_api_shapes_and_conventions(capi, tmp_path, monkeypatch):
     from Anis_TTF_rays import ALI_FMM

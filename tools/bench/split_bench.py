@@ -23,6 +23,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=16384)
     ap.add_argument("--out", default="")
+    ap.add_argument("--gpus", type=int, default=2)
     a = ap.parse_args()
     n = a.n
     m = models.voronoi(n, max(64, (n // 64) ** 2), 1235)
@@ -40,7 +41,7 @@ def main():
     for rep in range(2):
         t0 = time.perf_counter()
         two, c2 = _capi.ttf_split(m["veln"], m["velpn"], m["vel_map"], m["stif_den"], True, g, g.copy(), m["dnx"], src[0], src[1],
-                                  devices=(0, 1))
+                                  devices=tuple(range(a.gpus)))
         res.append((time.perf_counter() - t0, c2))
     w2, c2 = res[-1]
     nodes = n * n
@@ -49,8 +50,8 @@ def main():
             "bitwise_equal": bool(np.array_equal(one, two)),
             "one_gpu": {"ms_seq": c1["ms_seq"], "ms_march": c1["ms_march"], "rounds": c1["band_rounds"], "cluster_size": c1["cluster_size"],
                         "wall_s_first_call_without_model_upload": w1, "device_bytes": nodes * per_node_one},
-            "two_gpu_strips": {"ms_seq": c2["ms_seq"], "ms_march": c2["ms_march"], "rounds": c2["band_rounds"], "cluster_size": 8,
-                               "wall_s_with_model_upload": w2, "device_bytes_per_gpu": (nodes // 2) * per_node_one,
+            "strips": a.gpus, "two_gpu_strips": {"ms_seq": c2["ms_seq"], "ms_march": c2["ms_march"], "rounds": c2["band_rounds"], "cluster_size": 8,
+                               "wall_s_with_model_upload": w2, "device_bytes_per_gpu": (nodes // a.gpus) * per_node_one,
                                "us_per_round": 1e3 * c2["ms_march"] / max(1, c2["band_rounds"])},
             "node_solves_per_s_one_gpu": nodes / (1e-3 * (c1["ms_seq"] + c1["ms_march"])),
             "node_solves_per_s_two_gpu": nodes / (1e-3 * (c2["ms_seq"] + c2["ms_march"]))}
