@@ -2204,9 +2204,14 @@ extern "C" int alifmm_ttf_split(const alifmm_model_desc *d, int32_t n_dev, const
         if (d->velpn[i] < 0 || d->velpn[i] >= d->n_cols) return fail(ALIFMM_E_INVALID, "alifmm_ttf_split: velpn holds a material id outside the velocity tables");
 
     StripDev S[ALI_MAX_STRIPS];
-    int rc = ALIFMM_OK;
     std::string err;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    int ev_device = -1;
     auto cleanup = [&]() {
+        if (ev_device >= 0) {
+            cudaSetDevice(ev_device);
+            for (auto &e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
+        }
         for (StripDev &s : S) {
             if (s.device < 0) continue;
             cudaSetDevice(s.device);
@@ -2347,8 +2352,8 @@ extern "C" int alifmm_ttf_split(const alifmm_model_desc *d, int32_t n_dev, const
             A[k].nb[side].ctl = p.ctl; A[k].nb[side].lists = p.lists; A[k].nb[side].stage = p.stage;
         }
     }
-    cudaEvent_t ev[3];
     STRIP_TRY(cudaSetDevice(S[owner].device));
+    ev_device = S[owner].device;
     for (auto &e : ev) STRIP_TRY(cudaEventCreate(&e));
     STRIP_TRY(cudaEventRecord(ev[0], S[owner].stream));
     ali_seq_kernel<<<1, 32, 0, S[owner].stream>>>(A[owner].b);
@@ -2411,8 +2416,6 @@ extern "C" int alifmm_ttf_split(const alifmm_model_desc *d, int32_t n_dev, const
         counters->vmax = vmax; counters->delta = 0.35 * d->dnx / vmax;
         counters->cluster_size = 8; counters->seq_threads = 32;
     }
-    cudaSetDevice(S[owner].device);
-    for (auto &e : ev) cudaEventDestroy(e);
     cleanup();
 #undef STRIP_TRY
     return ALIFMM_OK;

@@ -187,7 +187,8 @@ int alifmm_eval_nodes(int device, int32_t n, int32_t nz, int32_t nx, double dnx,
  * on the data path).  The reference has no counterpart (one field is one heap); the result is bit-identical to alifmm_ttf()
  * on one device.  The value is capacity, not speed.  devices: n_dev distinct, mutually peer-accessible devices, strip k
  * (rows from the top) on devices[k]; split_row <= 0: automatic (equal shares, boundaries on multiples of 4, kept away
- * from the source so that its refined neighbourhood lies inside one strip), > 0 only with two devices; out_host
+ * from the source so that its refined neighbourhood lies inside one strip), > 0 only with two devices (rounded down to a
+ * multiple of 4; an inadmissible row is an error, not adjusted); out_host
  * [nz * nx]; counters may be NULL. */
 int alifmm_ttf_split(const alifmm_model_desc *desc, int32_t n_dev, const int32_t *devices, int32_t src_iz, int32_t src_ix,
                      int32_t split_row, double *out_host, alifmm_counters_t *counters);
