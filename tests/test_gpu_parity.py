@@ -509,6 +509,15 @@ def test_rays_through_same_field_match_oracle(capi, orc):
         assert ln[r] == len(ox) and fl[r] == of
         assert np.abs(x[r, :ln[r]] - ox).max() <= 1e-6 and np.abs(y[r, :ln[r]] - oy).max() <= 1e-6
         assert abs(tm[r] - ot) <= 1e-10 * ot
+    # the work queue hands the rays out longest-first whatever the caller's order, and the register-budget variants of
+    # the kernel (option ray_min_blocks) run the same arithmetic: a permuted, much longer job list gives the same rays
+    rng = np.random.default_rng(5)
+    pick = rng.integers(0, len(srcs), 700)
+    for mb in (4, 5, 6):
+        ctx.set_option("ray_min_blocks", mb)
+        x2, y2, ln2, tm2, fl2 = ctx.rays([srcs[q][0] for q in pick], [srcs[q][1] for q in pick], [0] * len(pick))
+        assert np.array_equal(ln2, ln[pick]) and np.array_equal(tm2, tm[pick]) and np.array_equal(fl2, fl[pick])
+        assert np.array_equal(x2, x[pick]) and np.array_equal(y2, y[pick])
     ctx.close()
 
 
