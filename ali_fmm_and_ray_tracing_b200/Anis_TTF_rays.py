@@ -365,6 +365,20 @@ class ALI_FMM:
             ctx.close()
         return out
 
+    def update_i_split(self, source_i, veln, velpn, vel_map, stif_den=None, devices=None):
+        """Travel time field of one source (``update_i`` at subgrid 1) on a grid too large for one GPU: the field
+        is cut into row strips, one per device (2 ... 8; default: the visible devices), which exchange their halo
+        and the per-round minimum over NVLink (``alifmm_ttf_split``; no counterpart in the reference, same bits as
+        ``update_i``)."""
+        if type(vel_map) == type(None):
+            vel_map = np.ones(veln.shape)
+        devices = list(_device_list() if devices is None else devices)[:8]
+        iz, ix = self._source_nodes([source_i])
+        out, counters = _capi.ttf_split(veln, velpn, vel_map, stif_den, True, self.velocity_dat, self.phase_vel, self.dnx,
+                                        int(iz[0]), int(ix[0]), devices=devices)
+        self.last_counters = [counters]
+        return out
+
     # ------------------------------------------------------------------ material tables
     def plot_phase(self, material_index=1):
         """Polar plot of a tabulated phase velocity curve (ATR:4090)."""

@@ -692,6 +692,13 @@ def test_two_gpu_strips_equal_one_gpu(capi):
             assert c2["band_rounds"] == c1["band_rounds"], (c1, c2)
             assert 0.99 * c1["band_evals"] <= c2["band_evals"] <= c1["band_evals"], (c1["band_evals"], c2["band_evals"])
         ctx.close()
+    # the class method (devices from set_devices / ALIFMM_DEVICES)
+    from Anis_TTF_rays import ALI_FMM
+    c = cases[1][0]
+    fm = ALI_FMM(c["veln"], c["velpn"], c["vel_map"], c["dnx"] * np.array([130.0]), np.array([0.0]), stif_den=c["stif_den"], dnx=c["dnx"])
+    a = fm.update_i(0, c["veln"], c["velpn"], c["vel_map"], stif_den=c["stif_den"])
+    b = fm.update_i_split(0, c["veln"], c["velpn"], c["vel_map"], stif_den=c["stif_den"], devices=[0, 1])
+    assert np.array_equal(a, b)
     with pytest.raises(RuntimeError):   # the source's refined neighbourhood would straddle the boundary
         m = cases[0][0]
         g, p = _tables(m)
