@@ -48,7 +48,7 @@ EXPORTS = [
     "alifmm_ttf", "alifmm_ttf_fetch", "alifmm_ttf_shape", "alifmm_rays", "alifmm_rays_into", "alifmm_trim",
     "alifmm_mem_info", "alifmm_counters",
     "alifmm_velocity_curves", "alifmm_min_max_vel", "alifmm_last_error",
-    "alifmm_velocity_curves_batch", "alifmm_eval_nodes", "alifmm_ttf_split",
+    "alifmm_velocity_curves_batch", "alifmm_eval_nodes", "alifmm_ttf_split", "alifmm_split_rows",
 ]
 
 _lib = None
@@ -94,6 +94,7 @@ def load():
                                       _i32p, _f64p, _f64p, _i32p]
     lib.alifmm_ttf_split.argtypes = [ctypes.POINTER(ModelDesc), ctypes.c_int32, _i32p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                      _f64p, ctypes.POINTER(Counters)]
+    lib.alifmm_split_rows.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _i32p]
     _lib = lib
     return lib
 
@@ -127,6 +128,13 @@ def velocity_curves_batch(materials, device=0):
     p = np.zeros((n, 361))
     _check(load().alifmm_velocity_curves_batch(int(device), n, _ptr(props, _f64p), _ptr(g, _f64p), _ptr(p, _f64p)))
     return g, p
+
+
+def split_rows(nz, n_dev, src_iz, split_row=-1):
+    """Rows of the strips ``ttf_split`` would use: n_dev + 1 boundaries (alifmm_split_rows; needs no device)."""
+    rows = np.zeros(int(n_dev) + 1 if 0 < int(n_dev) < 64 else 65, dtype=np.int32)
+    _check(load().alifmm_split_rows(int(nz), int(n_dev), int(src_iz), int(split_row), _ptr(rows, _i32p)))
+    return rows[:int(n_dev) + 1].tolist()
 
 
 def ttf_split(veln, velpn, vel_map, stif_den, has_stif, group_vel, phase_vel, dnx, src_iz, src_ix, devices=(0, 1), split_row=-1):

@@ -2161,6 +2161,38 @@ struct StripDev {
 };
 }
 
+// Rows owned by the strips of alifmm_ttf_split: strip k owns [rows[k], rows[k + 1]).  Equal shares, boundaries on multiples
+// of 4 (tile rows); a boundary closer to the source row than the sequential phase's window (hand-over radius + 8 rows)
+// is pushed away from it.  Pure host arithmetic (no device needed).
+extern "C" int alifmm_split_rows(int32_t nz, int32_t n_dev, int32_t src_iz, int32_t split_row, int32_t *rows)
+{
+    if (!rows) return fail(ALIFMM_E_INVALID, "alifmm_split_rows: null argument");
+    if (n_dev < 2 || n_dev > ALI_MAX_STRIPS) return fail(ALIFMM_E_INVALID, "alifmm_ttf_split: 2 ... 8 devices (a chain of row strips)");
+    if (nz < 64 || nz > 65535) return fail(ALIFMM_E_INVALID, "alifmm_ttf_split: 64 ... 65535 rows");
+    if (src_iz < 0 || src_iz >= nz) return fail(ALIFMM_E_INVALID, "alifmm_ttf_split: source node outside the grid");
+    if (split_row > 0 && n_dev != 2) return fail(ALIFMM_E_INVALID, "alifmm_ttf_split: an explicit split row only with two devices");
+    AliSourcePlan plan;
+    AliModel pm{}; pm.nz = nz; pm.nx = 64;
+    ali_make_plan(plan, pm, src_iz, 0, 1, 27);
+    const int keep = plan.stop_r + 8;   // the sequential phase's window (stop_r + 4 each way) must lie inside one strip
+    int *zb = rows;
+    zb[0] = 0; zb[n_dev] = nz;
+    for (int k = 1; k < n_dev; k++) zb[k] = (int)((long long)nz * k / n_dev) & ~3;
+    if (split_row > 0) zb[1] = split_row & ~3;
+    else
+        for (int k = 1; k < n_dev; k++) {
+            if (zb[k] <= src_iz && src_iz - zb[k] + 1 < keep) zb[k] = (src_iz - keep) & ~3;         // boundary above the source: up
+            else if (zb[k] > src_iz && zb[k] - src_iz < keep) zb[k] = (src_iz + keep + 3) & ~3;      // below: down
+        }
+    for (int k = 1; k < n_dev; k++) {
+        const bool near = zb[k] <= src_iz ? (src_iz - zb[k] + 1 < keep) : (zb[k] - src_iz < keep);
+        if (zb[k] < 8 || zb[k] > nz - 8 || zb[k] - zb[k - 1] < 16 || near)
+            return fail(ALIFMM_E_INVALID, "alifmm_ttf_split: no admissible split rows (strips of at least 16 rows, the source's refined neighbourhood inside one strip)");
+    }
+    if (nz - zb[n_dev - 1] < 8) return fail(ALIFMM_E_INVALID, "alifmm_ttf_split: no admissible split rows");
+    return ALIFMM_OK;
+}
+
 extern "C" int alifmm_ttf_split(const alifmm_model_desc *d, int32_t n_dev, const int32_t *devices, int32_t src_iz,
                                 int32_t src_ix, int32_t split_row, double *out_host, alifmm_counters_t *counters)
 {
@@ -2182,24 +2214,11 @@ extern "C" int alifmm_ttf_split(const alifmm_model_desc *d, int32_t n_dev, const
     AliSourcePlan plan;
     AliModel pm{}; pm.nz = nz; pm.nx = nx;
     ali_make_plan(plan, pm, src_iz, src_ix, 1, margin);
-    const int keep = plan.stop_r + 8;   // the sequential phase's window (stop_r + 4 each way) must lie inside one strip
-    // strip k owns rows [zb[k], zb[k + 1]): equal shares, boundaries on multiples of 4 (tile rows), the boundaries next
-    // to the source pushed away from it
     int zb[ALI_MAX_STRIPS + 1];
-    zb[0] = 0; zb[n_dev] = nz;
-    for (int k = 1; k < n_dev; k++) zb[k] = (int)((long long)nz * k / n_dev) & ~3;
-    if (split_row > 0) zb[1] = split_row & ~3;
-    else
-        for (int k = 1; k < n_dev; k++) {
-            if (zb[k] <= src_iz && src_iz - zb[k] + 1 < keep) zb[k] = (src_iz - keep) & ~3;         // boundary above the source: up
-            else if (zb[k] > src_iz && zb[k] - src_iz < keep) zb[k] = (src_iz + keep + 3) & ~3;      // below: down
-        }
-    for (int k = 1; k < n_dev; k++) {
-        const bool near = zb[k] <= src_iz ? (src_iz - zb[k] + 1 < keep) : (zb[k] - src_iz < keep);
-        if (zb[k] < 8 || zb[k] > nz - 8 || zb[k] - zb[k - 1] < 16 || near)
-            return fail(ALIFMM_E_INVALID, "alifmm_ttf_split: no admissible split rows (strips of at least 16 rows, the source's refined neighbourhood inside one strip)");
+    {
+        const int rrc = alifmm_split_rows(nz, n_dev, src_iz, split_row, zb);
+        if (rrc != ALIFMM_OK) return rrc;
     }
-    if (nz - zb[n_dev - 1] < 8) return fail(ALIFMM_E_INVALID, "alifmm_ttf_split: no admissible split rows");
     for (size_t i = 0; i < (size_t)nz * nx; i++)
         if (d->velpn[i] < 0 || d->velpn[i] >= d->n_cols) return fail(ALIFMM_E_INVALID, "alifmm_ttf_split: velpn holds a material id outside the velocity tables");
 

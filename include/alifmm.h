@@ -193,6 +193,10 @@ int alifmm_eval_nodes(int device, int32_t n, int32_t nz, int32_t nx, double dnx,
 int alifmm_ttf_split(const alifmm_model_desc *desc, int32_t n_dev, const int32_t *devices, int32_t src_iz, int32_t src_ix,
                      int32_t split_row, double *out_host, alifmm_counters_t *counters);
 
+/* The rows alifmm_ttf_split gives to its strips: rows[k] ... rows[k + 1] - 1 for strip k, rows[0] = 0, rows[n_dev] = nz
+ * (rows: n_dev + 1 entries).  Host arithmetic only; the same errors as alifmm_ttf_split for an inadmissible request. */
+int alifmm_split_rows(int32_t nz, int32_t n_dev, int32_t src_iz, int32_t split_row, int32_t *rows);
+
 const char *alifmm_last_error(void);
 
 #ifdef __cplusplus

@@ -174,3 +174,24 @@ def test_dense_ray_arrays_behave_like_numpy_zeros():
     copy = big.copy()
     del big, view                                  # the mapping goes away with the last reference
     assert copy[1, 2, 4] == 4.0
+
+
+def test_strip_rows_of_the_domain_decomposition(built_library):
+    """alifmm_split_rows (host arithmetic of alifmm_ttf_split): equal shares on multiples of 4 rows, boundaries kept
+    away from the source so that its sequential near-source window (hand-over radius 40 + 8 rows) lies in one strip."""
+    from ali_fmm_and_ray_tracing_b200 import _capi
+    assert _capi.split_rows(16384, 2, 4096) == [0, 8192, 16384]
+    assert _capi.split_rows(16384, 8, 100) == [0] + [2048 * k for k in range(1, 8)] + [16384]
+    assert _capi.split_rows(768, 2, 384) == [0, 336, 768]            # source on the first row below the boundary: pushed up
+    assert _capi.split_rows(768, 2, 383) == [0, 432, 768]            # source just above the boundary: pushed down
+    for nz, n, src in ((1536, 4, 385), (1536, 8, 1535), (4096, 3, 0), (640, 4, 320)):
+        rows = _capi.split_rows(nz, n, src)
+        assert rows[0] == 0 and rows[-1] == nz and len(rows) == n + 1
+        assert all(b % 4 == 0 for b in rows[1:-1]) and all(b - a >= 16 for a, b in zip(rows, rows[1:]))
+        owner = max(k for k in range(n) if rows[k] <= src)
+        assert src - rows[owner] + 1 >= 48 or owner == 0
+        assert rows[owner + 1] - src >= 48 or owner == n - 1
+    assert _capi.split_rows(768, 2, 10, split_row=601) == [0, 600, 768]
+    for bad in ((768, 2, 384, 380), (768, 1, 10, -1), (768, 9, 10, -1), (768, 4, 10, 300), (200, 8, 100, -1)):
+        with pytest.raises(_capi.AlifmmError):
+            _capi.split_rows(*bad[:3], split_row=bad[3])
