@@ -263,6 +263,12 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if args.config == "big16384" and world > 1 and rank != 0:
+        # (the decomposed single field is driven by rank 0 alone: no 17 GB model per rank)
+        dist.barrier()
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     cfg = make_config(args.config, args.sources)
     m, scx, scz, sg = cfg["model"], cfg["scx"], cfg["scz"], cfg["sg"]
     dnx = m["dnx"]
@@ -275,6 +281,12 @@ def run_gpu(args):
     ix_all = np.round(scx / dnx).astype(np.int32)
     shim.tqdm_disable = True
     set_devices([local])
+    if cfg["name"] == "big16384" and world > 1:
+        # BASELINE config 5 as stated: ONE field, domain-decomposed into row strips over the N GPUs (NVLink halo
+        # exchange, alifmm_ttf_split).  Rank 0 drives all N devices through the library; the other ranks only keep the
+        # launch contract (barrier, exit).
+        run_split(args, cfg, world, rank, local, dist, torch)
+        return
 
     def shard(scaling):
         """This rank's receivers and rays: (field transducer ids, pair matrix or source mask)."""
@@ -483,6 +495,71 @@ def run_gpu(args):
                                     "rays_per_s_per_core": r["rays"] / r["ray_core_s"] if r["ray_core_s"] > 0 else None}
         if args.parity:
             line["parity"] = parity_check(cfg, args, local)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_split(args, cfg, world, rank, local, dist, torch):
+    from ali_fmm_and_ray_tracing_b200 import _capi
+    m = cfg["model"]
+    dnx = m["dnx"]
+    nz, nx = m["veln"].shape
+    g_tab, p_tab = tables(m)
+    iz = int(round(float(cfg["scz"][0]) / dnx))
+    ix = int(round(float(cfg["scx"][0]) / dnx))
+    line = None
+    if rank == 0:
+        devices = tuple(range(world))
+
+        def call():
+            t0 = time.perf_counter()
+            _, c = _capi.ttf_split(m["veln"], m["velpn"], m["vel_map"], m["stif_den"], True, g_tab, p_tab, dnx, iz, ix, devices=devices)
+            return time.perf_counter() - t0, c
+
+        for _ in range(args.warmup):
+            call()
+        sampler = ClockSampler(local)
+        sampler.start()
+        walls, dev_ms, seq_ms, march_ms, launches, rounds = [], [], [], [], 0, 0
+        for _ in range(args.steps):
+            w, c = call()
+            walls.append(w)
+            seq_ms.append(c["ms_seq"]); march_ms.append(c["ms_march"]); dev_ms.append(c["ms_seq"] + c["ms_march"])
+            launches += c["kernel_launches"]
+            rounds = c["band_rounds"]
+        clocks = sampler.stop()
+        nodes = nz * nx
+        ms = statistics.mean(dev_ms)
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        achieved = (nodes / world) * B_ALG / (statistics.mean(march_ms) * 1e-3) / 1e9
+        line = base_line(cfg, args, world, "strong")
+        line.update({"value": nodes / (ms * 1e-3), "ms_per_step": ms})
+        line["config"].update({
+            "decomposition": "%d row strips, one per GPU; halo, claims and per-round minimum over NVLink peer memory (alifmm_ttf_split)" % world,
+            "fields_total": 1, "rays_total": 0, "ms_seq_kernel": statistics.mean(seq_ms), "ms_march_kernel": statistics.mean(march_ms),
+            "band_rounds_max": rounds, "march_ctas_per_source": 8, "device_bytes_per_gpu": (nodes // world) * 81,
+            "l2_policy": "inputs_larger_than_l2 (%.2f GB of field + model state per GPU)" % ((nodes // world) * 81 / 1e9),
+            "timing_note": "value: CUDA events around the sequential phase and the strip kernels on the source's device "
+                           "(all strips run in lockstep: three inter-GPU barriers per round); e2e: wall time of the call with host arrays "
+                           "(model strips up, field back)"})
+        line["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                            "kernel": "ali_march_strip_kernel", "peak_source": peak_src, "algorithmic_bytes_per_launch": (nodes / world) * B_ALG,
+                            "note": "per GPU.  Round-latency bound: %d rounds of three NVLink barriers each; the decomposition buys capacity, not speed" % rounds}
+        h2d = int(m["veln"].nbytes + m["veln"].size * 4 + m["vel_map"].nbytes + m["stif_den"].nbytes + 2 * g_tab.nbytes * world)
+        line["e2e"] = {"value": nodes / statistics.mean(walls), "unit": "node-solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": nodes * 8,
+                       "api": "alifmm_ttf_split (ALI_FMM.update_i_split)", "steps": args.steps, "s_per_step": statistics.mean(walls),
+                       "s_per_call": [round(t, 4) for t in walls]}
+        line["gpu_launches"] = launches
+        line["clocks"] = clocks
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
