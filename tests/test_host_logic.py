@@ -195,3 +195,22 @@ def test_strip_rows_of_the_domain_decomposition(built_library):
     for bad in ((768, 2, 384, 380), (768, 1, 10, -1), (768, 9, 10, -1), (768, 4, 10, 300), (200, 8, 100, -1)):
         with pytest.raises(_capi.AlifmmError):
             _capi.split_rows(*bad[:3], split_row=bad[3])
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """``bench.py --impl reference`` (the CPU arm the driver times next to the GPU arm) on the smallest config: one JSON
+    line with the contract's keys, the oracle port as ``cpu_baseline`` and an ``e2e`` object without copies."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "nb", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "impl", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["metric"] == "ttf_node_solves_per_s" and line["dtype"] == "f64"
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    assert line["value"] > 1e5 and "workload" in line["config"]
