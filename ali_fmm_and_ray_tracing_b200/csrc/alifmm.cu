@@ -2255,22 +2255,31 @@ extern "C" int alifmm_ttf_split(const alifmm_model_desc *d, int32_t n_dev, const
         seq_cap = lvl > w * w ? lvl : w * w;
         heap_cap = (int)(seq_cap / 2 + 64);
     }
-    for (int k = 0; k < n_dev; k++) {
+    // every strip is set up by its own host thread: the uploads of the strips' model rows (pageable host memory, one
+    // PCIe link per GPU) run side by side
+    std::string serr[ALI_MAX_STRIPS];
+    int src_codes[ALI_MAX_STRIPS] = {0};
+#define STRIP_TRY_K(expr)                                                                           \
+    do {                                                                                            \
+        cudaError_t e__ = (expr);                                                                   \
+        if (e__ != cudaSuccess) { serr[k] = std::string(#expr) + ": " + cudaGetErrorString(e__); return (int)ALIFMM_E_CUDA; } \
+    } while (0)
+    auto setup = [&](int k) -> int {
         StripDev &s = S[k];
         s.device = devices[k];
         s.zlo = zb[k]; s.zhi = zb[k + 1];
         s.za = k == 0 ? 0 : s.zlo - 4; s.zb = k == n_dev - 1 ? ((nz + 3) & ~3) : s.zhi + 4;
-        STRIP_TRY(cudaSetDevice(s.device));
+        STRIP_TRY_K(cudaSetDevice(s.device));
         for (int j = 0; j < n_dev; j++) {
             if (j == k) continue;
             int can = 0;
-            STRIP_TRY(cudaDeviceCanAccessPeer(&can, s.device, devices[j]));
-            if (!can) { cleanup(); return fail(ALIFMM_E_CUDA, "alifmm_ttf_split: the devices cannot access each other's memory"); }
+            STRIP_TRY_K(cudaDeviceCanAccessPeer(&can, s.device, devices[j]));
+            if (!can) { serr[k] = "the devices cannot access each other's memory"; return (int)ALIFMM_E_CUDA; }
             cudaError_t pe = cudaDeviceEnablePeerAccess(devices[j], 0);
-            if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) STRIP_TRY(pe);
+            if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) STRIP_TRY_K(pe);
             cudaGetLastError();
         }
-        STRIP_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        STRIP_TRY_K(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         auto alloc = [&](size_t bytes, void **out) -> cudaError_t {
             cudaError_t e = cudaMalloc(out, bytes < 256 ? 256 : bytes);
             if (e == cudaSuccess) s.allocs.push_back(*out);
@@ -2280,23 +2289,23 @@ extern "C" int alifmm_ttf_split(const alifmm_model_desc *d, int32_t n_dev, const
         const int r0 = s.za, r1 = s.zb < nz ? s.zb : nz;
         const size_t nn = (size_t)(r1 - r0) * nx, off = (size_t)r0 * nx;
         void *dv, *dp, *dm, *ds = nullptr, *drec, *dg, *dph, *dmod, *dbad;
-        STRIP_TRY(alloc(nn * 8, &dv)); STRIP_TRY(alloc(nn * 4, &dp)); STRIP_TRY(alloc(nn * 8, &dm));
-        if (d->stif_den) STRIP_TRY(alloc(nn * 40, &ds));
-        STRIP_TRY(alloc(nn * sizeof(AliMatRec), &drec)); STRIP_TRY(alloc(64, &dbad));
-        STRIP_TRY(cudaMemcpyAsync(dv, d->veln + off, nn * 8, cudaMemcpyHostToDevice, s.stream));
-        STRIP_TRY(cudaMemcpyAsync(dp, d->velpn + off, nn * 4, cudaMemcpyHostToDevice, s.stream));
-        STRIP_TRY(cudaMemcpyAsync(dm, d->vel_map + off, nn * 8, cudaMemcpyHostToDevice, s.stream));
-        if (ds) STRIP_TRY(cudaMemcpyAsync(ds, d->stif_den + off * 5, nn * 40, cudaMemcpyHostToDevice, s.stream));
-        STRIP_TRY(cudaMemsetAsync(dbad, 0, 64, s.stream));
+        STRIP_TRY_K(alloc(nn * 8, &dv)); STRIP_TRY_K(alloc(nn * 4, &dp)); STRIP_TRY_K(alloc(nn * 8, &dm));
+        if (d->stif_den) STRIP_TRY_K(alloc(nn * 40, &ds));
+        STRIP_TRY_K(alloc(nn * sizeof(AliMatRec), &drec)); STRIP_TRY_K(alloc(64, &dbad));
+        STRIP_TRY_K(cudaMemcpyAsync(dv, d->veln + off, nn * 8, cudaMemcpyHostToDevice, s.stream));
+        STRIP_TRY_K(cudaMemcpyAsync(dp, d->velpn + off, nn * 4, cudaMemcpyHostToDevice, s.stream));
+        STRIP_TRY_K(cudaMemcpyAsync(dm, d->vel_map + off, nn * 8, cudaMemcpyHostToDevice, s.stream));
+        if (ds) STRIP_TRY_K(cudaMemcpyAsync(ds, d->stif_den + off * 5, nn * 40, cudaMemcpyHostToDevice, s.stream));
+        STRIP_TRY_K(cudaMemsetAsync(dbad, 0, 64, s.stream));
         {
             int blocks = (int)((nn + 255) / 256);
             if (blocks > 148 * 8) blocks = 148 * 8;
             ali_records_kernel<<<blocks, 256, 0, s.stream>>>((int)nn, (const double *)dv, (const int32_t *)dp, (const double *)dm,
                                                             (const long long *)ds, (AliMatRec *)drec, (int *)dbad);
         }
-        STRIP_TRY(alloc((size_t)361 * d->n_cols * 8, &dg)); STRIP_TRY(alloc((size_t)361 * d->n_cols * 8, &dph));
-        STRIP_TRY(cudaMemcpyAsync(dg, d->group_vel, (size_t)361 * d->n_cols * 8, cudaMemcpyHostToDevice, s.stream));
-        STRIP_TRY(cudaMemcpyAsync(dph, d->phase_vel, (size_t)361 * d->n_cols * 8, cudaMemcpyHostToDevice, s.stream));
+        STRIP_TRY_K(alloc((size_t)361 * d->n_cols * 8, &dg)); STRIP_TRY_K(alloc((size_t)361 * d->n_cols * 8, &dph));
+        STRIP_TRY_K(cudaMemcpyAsync(dg, d->group_vel, (size_t)361 * d->n_cols * 8, cudaMemcpyHostToDevice, s.stream));
+        STRIP_TRY_K(cudaMemcpyAsync(dph, d->phase_vel, (size_t)361 * d->n_cols * 8, cudaMemcpyHostToDevice, s.stream));
         // the strip's own maximum of the phase velocity (on its rows, with a strip-local model view)
         AliModel ml{};
         ml.nz = r1 - r0; ml.nx = nx; ml.rec = (const AliMatRec *)drec; ml.has_stif = d->has_stif ? 1 : 0;
@@ -2308,37 +2317,47 @@ extern "C" int alifmm_ttf_split(const alifmm_model_desc *d, int32_t n_dev, const
             ali_vmax_kernel<<<blocks, 256, 0, s.stream>>>(ml, dvmax);
         }
         unsigned long long hb[2] = {0, 0};
-        STRIP_TRY(cudaMemcpyAsync(hb, dbad, 16, cudaMemcpyDeviceToHost, s.stream));
-        STRIP_TRY(cudaStreamSynchronize(s.stream));
-        if ((int)hb[0]) { cleanup(); return fail(ALIFMM_E_INVALID, "alifmm_ttf_split: veln / vel_map hold non-finite values"); }
+        STRIP_TRY_K(cudaMemcpyAsync(hb, dbad, 16, cudaMemcpyDeviceToHost, s.stream));
+        STRIP_TRY_K(cudaStreamSynchronize(s.stream));
+        if ((int)hb[0]) { serr[k] = "veln / vel_map hold non-finite values"; return (int)ALIFMM_E_INVALID; }
         memcpy(&s.vmax, &hb[1], 8);
         // the march's model: full-grid extents, records offset so that (z * nx + x) indexes the strip's rows
         s.m = ml; s.m.nz = nz; s.m.rec = (const AliMatRec *)drec - off;
-        STRIP_TRY(alloc(sizeof(AliModel), &dmod));
-        STRIP_TRY(cudaMemcpyAsync(dmod, &s.m, sizeof(AliModel), cudaMemcpyHostToDevice, s.stream));
+        STRIP_TRY_K(alloc(sizeof(AliModel), &dmod));
+        STRIP_TRY_K(cudaMemcpyAsync(dmod, &s.m, sizeof(AliModel), cudaMemcpyHostToDevice, s.stream));
         s.m_dev = (const AliModel *)dmod;
         // field strip (tiled), alive flags, result rows, lists, control / exchange blocks, record
         const size_t tn = (size_t)((s.zb - s.za) >> 2) * t4x * 16;
-        STRIP_TRY(alloc(tn * 8, (void **)&s.Tt)); STRIP_TRY(alloc(tn + 16, (void **)&s.st));
-        STRIP_TRY(alloc((size_t)(s.zhi - s.zlo) * nx * 8, (void **)&s.out));
-        STRIP_TRY(alloc((size_t)4 * band_cap * 4, (void **)&s.lists)); STRIP_TRY(alloc((size_t)2 * band_cap * 8, (void **)&s.stage));
-        STRIP_TRY(alloc(sizeof(AliClusterCtl), (void **)&s.ctl)); STRIP_TRY(alloc(ALI_MAX_STRIPS * sizeof(AliStripXchg), (void **)&s.xchg));
-        STRIP_TRY(alloc(sizeof(AliSourceRec), (void **)&s.rec));
-        STRIP_TRY(cudaMemsetAsync(s.Tt, ALI_T_UNSET_BYTE, tn * 8, s.stream));
-        STRIP_TRY(cudaMemsetAsync(s.st, 0, tn + 16, s.stream));
-        STRIP_TRY(cudaMemsetAsync(s.ctl, 0, sizeof(AliClusterCtl), s.stream));
-        STRIP_TRY(cudaMemsetAsync(s.xchg, 0, ALI_MAX_STRIPS * sizeof(AliStripXchg), s.stream));
+        STRIP_TRY_K(alloc(tn * 8, (void **)&s.Tt)); STRIP_TRY_K(alloc(tn + 16, (void **)&s.st));
+        STRIP_TRY_K(alloc((size_t)(s.zhi - s.zlo) * nx * 8, (void **)&s.out));
+        STRIP_TRY_K(alloc((size_t)4 * band_cap * 4, (void **)&s.lists)); STRIP_TRY_K(alloc((size_t)2 * band_cap * 8, (void **)&s.stage));
+        STRIP_TRY_K(alloc(sizeof(AliClusterCtl), (void **)&s.ctl)); STRIP_TRY_K(alloc(ALI_MAX_STRIPS * sizeof(AliStripXchg), (void **)&s.xchg));
+        STRIP_TRY_K(alloc(sizeof(AliSourceRec), (void **)&s.rec));
+        STRIP_TRY_K(cudaMemsetAsync(s.Tt, ALI_T_UNSET_BYTE, tn * 8, s.stream));
+        STRIP_TRY_K(cudaMemsetAsync(s.st, 0, tn + 16, s.stream));
+        STRIP_TRY_K(cudaMemsetAsync(s.ctl, 0, sizeof(AliClusterCtl), s.stream));
+        STRIP_TRY_K(cudaMemsetAsync(s.xchg, 0, ALI_MAX_STRIPS * sizeof(AliStripXchg), s.stream));
         AliSourceRec hr;
         memset(&hr, 0, sizeof hr);
         hr.src_iz = src_iz; hr.src_ix = src_ix;
-        STRIP_TRY(cudaMemcpyAsync(s.rec, &hr, sizeof hr, cudaMemcpyHostToDevice, s.stream));
+        STRIP_TRY_K(cudaMemcpyAsync(s.rec, &hr, sizeof hr, cudaMemcpyHostToDevice, s.stream));
         if (k == owner) {
-            STRIP_TRY(alloc(2 * seq_cap * 8, (void **)&s.seq_t)); STRIP_TRY(alloc(2 * seq_cap * 4, (void **)&s.seq_s));
-            STRIP_TRY(alloc((size_t)2 * heap_cap * 4, (void **)&s.seq_heap)); STRIP_TRY(alloc(ALI_HKEY_SLOTS(heap_cap) * 8, (void **)&s.seq_hkey));
-            STRIP_TRY(alloc(seq_cap * 8, (void **)&s.seq_cval)); STRIP_TRY(alloc(seq_cap + 16, (void **)&s.seq_cflag));
+            STRIP_TRY_K(alloc(2 * seq_cap * 8, (void **)&s.seq_t)); STRIP_TRY_K(alloc(2 * seq_cap * 4, (void **)&s.seq_s));
+            STRIP_TRY_K(alloc((size_t)2 * heap_cap * 4, (void **)&s.seq_heap)); STRIP_TRY_K(alloc(ALI_HKEY_SLOTS(heap_cap) * 8, (void **)&s.seq_hkey));
+            STRIP_TRY_K(alloc(seq_cap * 8, (void **)&s.seq_cval)); STRIP_TRY_K(alloc(seq_cap + 16, (void **)&s.seq_cflag));
         }
-        STRIP_TRY(cudaStreamSynchronize(s.stream));
+        STRIP_TRY_K(cudaStreamSynchronize(s.stream));
+    
+        return (int)ALIFMM_OK;
+    };
+    {
+        std::vector<std::thread> workers;
+        for (int k = 0; k < n_dev; k++) workers.emplace_back([&, k]() { src_codes[k] = setup(k); });
+        for (std::thread &w : workers) w.join();
     }
+#undef STRIP_TRY_K
+    for (int k = 0; k < n_dev; k++)
+        if (src_codes[k] != ALIFMM_OK) { cleanup(); return fail(src_codes[k], "alifmm_ttf_split: " + serr[k]); }
     double vmax = 0.0;
     for (int k = 0; k < n_dev; k++) vmax = S[k].vmax > vmax ? S[k].vmax : vmax;
     if (!(vmax > 0) || !isfinite(vmax)) { cleanup(); return fail(ALIFMM_E_INVALID, "alifmm_ttf_split: model has no positive finite phase velocity"); }
@@ -2412,9 +2431,17 @@ extern "C" int alifmm_ttf_split(const alifmm_model_desc *d, int32_t n_dev, const
         if (ovf & 2) return fail(ALIFMM_E_CAPACITY, "alifmm_ttf_split: narrow-band list overflowed");
         return fail(ALIFMM_E_CAPACITY, "alifmm_ttf_split: sequential near-source scratch overflowed");
     }
-    for (int k = 0; k < n_dev; k++) {
-        STRIP_TRY(cudaSetDevice(S[k].device));
-        STRIP_TRY(cudaMemcpy(out_host + (size_t)S[k].zlo * nx, S[k].out, (size_t)(S[k].zhi - S[k].zlo) * nx * 8, cudaMemcpyDeviceToHost));
+    {   // the strips' rows come back side by side as well
+        cudaError_t cerr[ALI_MAX_STRIPS];
+        std::vector<std::thread> workers;
+        for (int k = 0; k < n_dev; k++)
+            workers.emplace_back([&, k]() {
+                cerr[k] = cudaSetDevice(S[k].device);
+                if (cerr[k] == cudaSuccess)
+                    cerr[k] = cudaMemcpy(out_host + (size_t)S[k].zlo * nx, S[k].out, (size_t)(S[k].zhi - S[k].zlo) * nx * 8, cudaMemcpyDeviceToHost);
+            });
+        for (std::thread &w : workers) w.join();
+        for (int k = 0; k < n_dev; k++) STRIP_TRY(cerr[k]);
     }
     if (counters) {
         memset(counters, 0, sizeof *counters);
