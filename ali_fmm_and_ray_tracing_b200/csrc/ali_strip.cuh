@@ -145,8 +145,10 @@ __global__ void __launch_bounds__(NT) ali_march_strip_kernel(AliStripArgs a)
     unsigned my_evals = 0, my_fbs = 0;
     int cur = 0;
     while (alive) {
-        const int n = ali_ldv(&ctl->count[cur]);
-        const int nwork = ali_ldv(&ctl->nwork[cur]);
+        // (after a list overflow the counters may exceed the capacity: the strips leave the loop together in phase C of
+        // this round, once the flag has travelled; until then stay inside the arrays)
+        const int n = min(ali_ldv(&ctl->count[cur]), cap);
+        const int nwork = min(ali_ldv(&ctl->nwork[cur]), cap);
         double *val = cur == 0 ? val0 : val1, *nval = cur == 0 ? val1 : val0;
         unsigned *ent = cur == 0 ? ent0 : ent1, *nent = cur == 0 ? ent1 : ent0;
         unsigned *wrk = cur == 0 ? wrk0 : wrk1, *nwrk = cur == 0 ? wrk1 : wrk0;

@@ -2335,6 +2335,8 @@ extern "C" int alifmm_ttf_split(const alifmm_model_desc *d, int32_t n_dev, const
         STRIP_TRY_K(alloc(sizeof(AliSourceRec), (void **)&s.rec));
         STRIP_TRY_K(cudaMemsetAsync(s.Tt, ALI_T_UNSET_BYTE, tn * 8, s.stream));
         STRIP_TRY_K(cudaMemsetAsync(s.st, 0, tn + 16, s.stream));
+        STRIP_TRY_K(cudaMemsetAsync(s.lists, 0, (size_t)4 * band_cap * 4, s.stream));   // (stale slots must stay valid indices after an overflow)
+        STRIP_TRY_K(cudaMemsetAsync(s.stage, 0, (size_t)2 * band_cap * 8, s.stream));
         STRIP_TRY_K(cudaMemsetAsync(s.ctl, 0, sizeof(AliClusterCtl), s.stream));
         STRIP_TRY_K(cudaMemsetAsync(s.xchg, 0, ALI_MAX_STRIPS * sizeof(AliStripXchg), s.stream));
         AliSourceRec hr;
